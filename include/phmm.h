@@ -1,0 +1,164 @@
+/*
+ * phmm.h -- C ABI of libphmm_sm100.so: batched pair-HMM realignment on B200.
+ *
+ * This is the drop-in boundary for the reference's realignment hot path.  The
+ * reference has no FFI there: it forks one `cactus_realign` process per mapped
+ * read and talks to it through argv, stdin and temp files
+ * (reference nanopore/analyses/utils.py:576-589, call at :587).  Each entry
+ * point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no C++/torch types;
+ *   - return 0 = OK, negative = error; text via phmm_last_error(ctx);
+ *   - inputs are caller-owned host memory, read-only, may be freed on return;
+ *   - outputs returned through `**` are owned by the library until phmm_free;
+ *   - a ctx is bound to one CUDA device and is single-threaded (one ctx per
+ *     GPU / rank); there are no callbacks;
+ *   - there is NO CPU fallback: phmm_create fails if no CUDA device answers.
+ *
+ * Encodings
+ *   bases    uint8: A=0 C=1 G=2 T=3, anything else 4            
+ *   cigar op uint32: (length << 2) | code, code 0=M 1=I 2=D, the SAM codes the
+ *            reference writes straight back into the record  (utils.py:173,602)
+ *   HMM      trans[25] row-major from*5+to, emis[80] = state*16 + x*4 + y with
+ *            x the reference base          (nanopore/mappers/blasr_hmm_0.txt:1-2)
+ *   states   0 match, 1 shortGapX, 2 shortGapY, 3 longGapX, 4 longGapY; X is
+ *            the reference, Y the read                            (utils.py:617)
+ */
+#ifndef PHMM_H
+#define PHMM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHMM_VERSION 1
+
+#define PHMM_OK 0
+#define PHMM_E_ARG (-1)      /* bad argument (odd band, cigar does not span the sequences, ...) */
+#define PHMM_E_CUDA (-2)     /* CUDA runtime error */
+#define PHMM_E_NOMEM (-3)    /* device or host allocation failed */
+#define PHMM_E_STATE (-4)    /* call order (no reference set, nothing prepared, ...) */
+
+typedef struct phmm_ctx phmm_ctx;
+
+/* Knobs of one cactus_realign invocation (utils.py:587) plus the upstream
+ * defaults the reference never overrides. */
+typedef struct phmm_params {
+    int32_t band;             /* --diagonalExpansion; even, >= 0         utils.py:587 passes 10 */
+    int32_t anchor_trim;      /* constraintDiagonalTrim; upstream default 14 */
+    int64_t split_side;       /* --splitMatrixBiggerThanThis (a side, squared internally) :587 passes 3000 */
+    int32_t min_diags;        /* minDiagsBetweenTraceBack; upstream 1000 */
+    int32_t tb_diags;         /* traceBackDiagonals; upstream 40 */
+    double threshold;         /* posterior match threshold; upstream 0.01 */
+    double gap_gamma;         /* --gapGamma    abstractMapper.py:25 default 0.5 */
+    double match_gamma;       /* --matchGamma  abstractMapper.py:25 default 0.0 */
+} phmm_params;
+
+/* Posterior match probabilities >= threshold, the content of
+ * --outputAllPosteriorProbs (marginAlignSnpCaller.py:136-149: lines
+ * "refPos readPos prob").  Sorted by (read, ref_pos, read_pos); prob is in
+ * units of 1e-7 as upstream quantises it. */
+typedef struct phmm_posteriors {
+    int64_t n;
+    int64_t *off;             /* n_reads+1 offsets into the arrays below */
+    int32_t *ref_pos;         /* relative to ref_start[read] */
+    int32_t *read_pos;
+    int32_t *prob_1e7;
+} phmm_posteriors;
+
+/* Work and time of the last prepared/run batch. */
+typedef struct phmm_batch_stats {
+    int64_t n_reads;
+    int64_t n_regions;        /* DP sub-problems after splitting at large anchor-free blocks */
+    int64_t cells;            /* DP cells (5 states each) = sum of band diagonal widths */
+    int64_t diagonals;
+    int64_t pairs;            /* posterior pairs emitted */
+    int64_t launches;         /* kernels launched by the last run */
+    double ms_geometry;       /* CUDA-event times on the library's stream */
+    double ms_fwdbwd;
+    double ms_decode;
+    double ms_total;
+    int64_t slot_bytes;       /* forward-window scratch per resident thread block */
+    int64_t n_slots;
+} phmm_batch_stats;
+
+int phmm_version(void);
+
+/* Fills p with what the reference passes / upstream defaults. */
+void phmm_default_params(phmm_params *p);
+
+/* Replaces: process start of cactus_realign incl. `--loadHmm=F` (utils.py:586-587)
+ * and Hmm.loadHmm (utils.py:534).  trans/emis NULL selects the stock 5-state
+ * model used when the reference passes no --loadHmm (abstractMapper.py:36-37).
+ * model_type: 0 fiveState, 1 fiveStateAsymmetric (only these two exist here).
+ * device: CUDA ordinal.  Returns NULL on failure (see phmm_create_error). */
+phmm_ctx *phmm_create(int device, const double *trans, const double *emis, int model_type);
+const char *phmm_create_error(void);
+void phmm_destroy(phmm_ctx *ctx);
+const char *phmm_last_error(phmm_ctx *ctx);
+
+/* Swap the HMM (next EM iteration; replaces re-launching with a new --loadHmm). */
+int phmm_set_model(phmm_ctx *ctx, const double *trans, const double *emis, int model_type);
+
+/* Replaces: writing the whole reference FASTA next to every job
+ * (utils.py:570,582).  Uploads once; ref_start/ref_end index into it, so
+ * several contigs may be concatenated by the caller. */
+int phmm_set_reference(phmm_ctx *ctx, const uint8_t *bases, int64_t n);
+
+/* Replaces: the fan-out/fan-in of one cactus_realign per read
+ * (utils.py:557-609).  For read i: Y = read_bases[read_off[i]..read_off[i+1]),
+ * X = reference[ref_start[i]..ref_end[i]), guide alignment
+ * in_cigar_ops[in_cigar_off[i]..in_cigar_off[i+1]) which must consume X and Y
+ * exactly (the chained-global invariant asserted at utils.py:381-382).
+ * Output: realigned ops for read i at (*out_cigar_ops)[(*out_cigar_off)[i] ..
+ * (*out_cigar_off)[i+1]), spanning X and Y exactly, in input order
+ * (utils.py:597).  post may be NULL. */
+int phmm_realign_batch(phmm_ctx *ctx, int64_t n_reads,
+                       const uint8_t *read_bases, const int64_t *read_off,
+                       const int64_t *ref_start, const int64_t *ref_end,
+                       const uint32_t *in_cigar_ops, const int64_t *in_cigar_off,
+                       const phmm_params *params,
+                       uint32_t **out_cigar_ops, int64_t **out_cigar_off,
+                       phmm_posteriors *post);
+
+/* Replaces: `cactus_realign --outputExpectations` over all alignments of one
+ * EM iteration (utils.py:528 via cactus_expectationMaximisation).
+ * out_stats[0..24] transition expectations from*5+to, [25..104] emission
+ * expectations state*16+x*4+y, [105] summed log-likelihood. Values are ADDED
+ * to nothing: the array is overwritten with this batch's sums, accumulated in
+ * read order so that shards can be combined deterministically. */
+int phmm_expectations_batch(phmm_ctx *ctx, int64_t n_reads,
+                            const uint8_t *read_bases, const int64_t *read_off,
+                            const int64_t *ref_start, const int64_t *ref_end,
+                            const uint32_t *in_cigar_ops, const int64_t *in_cigar_off,
+                            const phmm_params *params, double out_stats[106]);
+
+/* Split form of phmm_realign_batch for callers that keep a batch resident in
+ * HBM (bench.py's kernel-only `value`): prepare = host planning + H2D +
+ * geometry kernel + scratch allocation; run = forward/backward/posterior and
+ * decode kernels only, inputs and outputs resident in HBM; fetch = D2H + CIGAR
+ * assembly.  run may be repeated. */
+int phmm_batch_prepare(phmm_ctx *ctx, int64_t n_reads,
+                       const uint8_t *read_bases, const int64_t *read_off,
+                       const int64_t *ref_start, const int64_t *ref_end,
+                       const uint32_t *in_cigar_ops, const int64_t *in_cigar_off,
+                       const phmm_params *params);
+int phmm_batch_run(phmm_ctx *ctx);
+int phmm_batch_fetch(phmm_ctx *ctx, uint32_t **out_cigar_ops, int64_t **out_cigar_off, phmm_posteriors *post);
+int phmm_batch_get_stats(phmm_ctx *ctx, phmm_batch_stats *out);
+
+/* Upper bound on device bytes the library may hold for scratch (0 = 80% of
+ * free memory at first use). */
+int phmm_set_memory_budget(phmm_ctx *ctx, int64_t bytes);
+
+/* Frees anything returned through an out pointer (ops, offsets, posterior arrays). */
+void phmm_free(void *p);
+void phmm_free_posteriors(phmm_posteriors *post);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHMM_H */

@@ -1,0 +1,781 @@
+// phmm_api.cu -- host side of libphmm_sm100.so: the C ABI of include/phmm.h.
+//
+// Replaces the per-read process fan-out of the reference
+// (nanopore/analyses/utils.py:557-609): guide cigars are turned into anchor
+// runs and DP regions on the host (integer work, O(#cigar ops)), everything
+// else runs in the kernels of phmm_kernels.cuh.  There is no CPU fallback and
+// nothing here links or calls oracle/.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/phmm.h"
+#include "phmm_kernels.cuh"
+
+using namespace phmm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct BatchState {
+    bool prepared = false, ran = false, expect = false;
+    int64_t n_reads = 0;
+    phmm_params params;
+    DevParams dp;
+    std::vector<Region> regions;
+    std::vector<Run> runs;
+    std::vector<RegionGeom> geom;
+    std::vector<int32_t> order;
+    std::vector<int64_t> read_first_region;   // n_reads + 1
+    std::vector<int64_t> read_lx, read_ly;
+    int nw = 1;
+    int fb_slots = 0, dec_slots = 0;
+    int64_t ring_cells = 0; int32_t dcap = 0, bw = 0;
+    int32_t max_lx = 0, max_ly = 0, max_nd = 0, max_pairs = 0;
+    int64_t total_pair_cap = 0, total_mrun_cap = 0;
+    int pair_factor = 8;
+    phmm_batch_stats stats;
+};
+
+}  // namespace
+
+struct phmm_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    DevModel model;
+    int64_t mem_budget = 0;
+    DevBuf d_ref; int64_t ref_len = -1;
+    DevBuf d_reads, d_regions, d_runs, d_geom, d_order, d_counter;
+    DevBuf d_fring, d_dtab, d_bring, d_dots;
+    DevBuf d_px, d_py, d_pw, d_npairs;
+    DevBuf d_expT, d_expE, d_expLL;
+    DevBuf d_sumx, d_sumy, d_dstart, d_dfill, d_sidx, d_wre, d_pred, d_colmap, d_sring, d_lring;
+    DevBuf d_mrx, d_mry, d_mrn, d_nmruns, d_score;
+    DevBuf d_cx, d_cy, d_cn, d_coff;
+    BatchState b;
+};
+
+namespace {
+
+int fail(phmm_ctx *ctx, int code, const std::string &msg) {
+    ctx->err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            (void)cudaGetLastError();                                                              \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? PHMM_E_NOMEM : PHMM_E_CUDA,         \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                       \
+        }                                                                                          \
+    } while (0)
+
+const double NEG_INF = -INFINITY;
+
+// stateMachine5 in log space
+void build_model(DevModel &m, const double *trans, const double *emis) {
+    memset(&m, 0, sizeof(m));
+    if (!trans || !emis) {
+        for (int i = 0; i < 25; i++) m.tr[i] = NEG_INF;
+        m.tr[S_M * 5 + S_M] = -0.030064059121770816;
+        m.tr[S_SX * 5 + S_M] = m.tr[S_SY * 5 + S_M] = -1.272871422049609;
+        m.tr[S_LX * 5 + S_M] = m.tr[S_LY * 5 + S_M] = -5.673280173170473;
+        m.tr[S_M * 5 + S_SX] = m.tr[S_M * 5 + S_SY] = -4.34381910900448;
+        m.tr[S_SX * 5 + S_SX] = m.tr[S_SY * 5 + S_SY] = -0.3388262689231553;
+        m.tr[S_SX * 5 + S_SY] = m.tr[S_SY * 5 + S_SX] = -4.910694825551255;
+        m.tr[S_M * 5 + S_LX] = m.tr[S_M * 5 + S_LY] = -6.30810595366929;
+        m.tr[S_LX * 5 + S_LX] = m.tr[S_LY * 5 + S_LY] = -0.003442492794189331;
+        for (int x = 0; x < 4; x++) {
+            for (int y = 0; y < 4; y++) {
+                double v = -4.5691014376830479;                       // transversion
+                if (x == y) v = -2.1149196655034745;
+                else if ((x ^ y) == 2) v = -3.9833860032220842;       // A<->G, C<->T
+                m.eM[x * 5 + y] = v;
+            }
+            m.eX[x] = m.eY[x] = -1.6094379124341003;
+        }
+    } else {
+        for (int i = 0; i < 25; i++) m.tr[i] = log(trans[i]);
+        for (int x = 0; x < 4; x++) for (int y = 0; y < 4; y++) m.eM[x * 5 + y] = log(emis[x * 4 + y]);
+        // gap emissions: marginal of the 4x4 tables of both gap states of a kind, normalised
+        double gx[4] = {0, 0, 0, 0}, gy[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) { gx[i] += emis[S_SX * 16 + i * 4 + j]; gx[i] += emis[S_LX * 16 + i * 4 + j]; }
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) { gy[j] += emis[S_SY * 16 + i * 4 + j]; gy[j] += emis[S_LY * 16 + i * 4 + j]; }
+        double tx = 0.0, ty = 0.0;
+        for (int i = 0; i < 4; i++) { tx += gx[i]; ty += gy[i]; }
+        for (int i = 0; i < 4; i++) { m.eX[i] = log(gx[i] / tx); m.eY[i] = log(gy[i] / ty); }
+    }
+    for (int i = 0; i < 5; i++) m.eM[4 * 5 + i] = m.eM[i * 5 + 4] = -2.772588722;   // N: log(1/16)
+    m.eX[4] = m.eY[4] = -1.386294361;                                               // N: log(1/4)
+    for (int s = 0; s < 5; s++) m.endp[s] = m.tr[s * 5 + S_M];
+    m.rendp[S_M] = m.tr[S_M * 5 + S_LX];
+    m.rendp[S_SX] = m.tr[S_M * 5 + S_LX];
+    m.rendp[S_SY] = m.tr[S_M * 5 + S_LY];
+    m.rendp[S_LX] = m.tr[S_LX * 5 + S_LX];
+    m.rendp[S_LY] = m.tr[S_LY * 5 + S_LY];
+    m.has_switch = (m.tr[S_SX * 5 + S_SY] != NEG_INF || m.tr[S_SY * 5 + S_SX] != NEG_INF) ? 1 : 0;
+}
+
+int check_params(phmm_ctx *ctx, const phmm_params *p) {
+    if (!p) return fail(ctx, PHMM_E_ARG, "params is NULL");
+    if (p->band < 0 || (p->band & 1)) return fail(ctx, PHMM_E_ARG, "band (diagonalExpansion) must be even and >= 0");
+    if (p->anchor_trim < 0) return fail(ctx, PHMM_E_ARG, "anchor_trim must be >= 0");
+    if (p->split_side < 1) return fail(ctx, PHMM_E_ARG, "split_side must be >= 1");
+    if (p->tb_diags < 1 || p->tb_diags + 2 > 256) return fail(ctx, PHMM_E_ARG, "tb_diags must be in [1, 254]");
+    if (p->min_diags < 2 || p->tb_diags + 1 >= p->min_diags)
+        return fail(ctx, PHMM_E_ARG, "need min_diags >= 2 and tb_diags + 1 < min_diags");
+    if (!(p->threshold >= 0.0 && p->threshold <= 1.0)) return fail(ctx, PHMM_E_ARG, "threshold must be in [0,1]");
+    return PHMM_OK;
+}
+
+// Splits one anchor-free block if its area exceeds side^2 (getSplitPoints).
+struct SplitState { int64_t x1 = 0, y1 = 0; std::vector<int64_t> quads; };
+
+void split_block(SplitState &s, int64_t x2, int64_t y2, int64_t x3, int64_t y3, int64_t side) {
+    const int64_t bx = x3 - x2, by = y3 - y2;
+    if (bx * by > side * side) {
+        const int64_t hx = std::min(bx / 2, side), hy = std::min(by / 2, side);
+        s.quads.insert(s.quads.end(), {s.x1, s.y1, x2 + hx, y2 + hy});
+        s.x1 = x3 - hx; s.y1 = y3 - hy;
+    }
+}
+
+// Host planning of one read: guide cigar -> anchor runs -> regions.
+int plan_read(phmm_ctx *ctx, int64_t read, const uint32_t *ops, int64_t nops, int64_t lX, int64_t lY,
+              int64_t ref_abs, int64_t read_abs, const phmm_params &p, std::vector<Region> &regions, std::vector<Run> &runs) {
+    struct ARun { int64_t x, y, n; };
+    std::vector<ARun> ar;
+    int64_t x = 0, y = 0;
+    for (int64_t i = 0; i < nops; i++) {
+        const int64_t len = ops[i] >> 2; const int code = ops[i] & 3;
+        if (code == 0) {
+            if (len > 2 * (int64_t)p.anchor_trim) ar.push_back({x + p.anchor_trim, y + p.anchor_trim, len - 2 * p.anchor_trim});
+            x += len; y += len;
+        } else if (code == 1) y += len;
+        else if (code == 2) x += len;
+        else return fail(ctx, PHMM_E_ARG, "cigar op code 3 is not M/I/D (read " + std::to_string(read) + ")");
+    }
+    if (x != lX || y != lY)
+        return fail(ctx, PHMM_E_ARG, "guide cigar of read " + std::to_string(read) + " spans " + std::to_string(x) + "x" +
+                                         std::to_string(y) + " but the sequences are " + std::to_string(lX) + "x" + std::to_string(lY));
+    // strictly increasing anchors are implied by a single cigar; merge touching runs
+    SplitState sp;
+    int64_t x2 = 0, y2 = 0;
+    for (const ARun &r : ar) {
+        split_block(sp, x2, y2, r.x, r.y, p.split_side);
+        x2 = r.x + r.n; y2 = r.y + r.n;
+    }
+    split_block(sp, x2, y2, lX, lY, p.split_side);
+    sp.quads.insert(sp.quads.end(), {sp.x1, sp.y1, lX, lY});
+    const size_t nreg = sp.quads.size() / 4;
+    size_t j = 0;
+    for (size_t i = 0; i < nreg; i++) {
+        Region g;
+        memset(&g, 0, sizeof(g));
+        const int64_t x1 = sp.quads[4 * i], y1 = sp.quads[4 * i + 1], xe = sp.quads[4 * i + 2], ye = sp.quads[4 * i + 3];
+        if (xe - x1 > 0x3fffffff || ye - y1 > 0x3fffffff) return fail(ctx, PHMM_E_ARG, "region too large");
+        g.xoff = ref_abs + x1; g.yoff = read_abs + y1;
+        g.lx = (int32_t)(xe - x1); g.ly = (int32_t)(ye - y1);
+        g.read = (int32_t)read; g.x1 = (int32_t)x1; g.y1 = (int32_t)y1;
+        g.ragged_left = i > 0; g.ragged_right = i + 1 < nreg;
+        g.run0 = (int32_t)runs.size();
+        while (j < ar.size() && ar[j].x + ar[j].y < xe + ye) {
+            const ARun &r = ar[j];
+            if (r.x < x1 || r.y < y1 || r.x + r.n > xe || r.y + r.n > ye)
+                return fail(ctx, PHMM_E_ARG, "anchor run crosses a region boundary (read " + std::to_string(read) + ")");
+            runs.push_back({(int32_t)(r.x - x1), (int32_t)(r.y - y1), (int32_t)r.n});
+            j++;
+        }
+        g.nrun = (int32_t)runs.size() - g.run0;
+        regions.push_back(g);
+    }
+    if (j != ar.size()) return fail(ctx, PHMM_E_ARG, "unassigned anchors (read " + std::to_string(read) + ")");
+    return PHMM_OK;
+}
+
+template <int NW>
+int launch_fwdbwd(phmm_ctx *ctx, const FbArgs &a, int slots, bool expect) {
+    const bool sw = ctx->model.has_switch != 0;
+    if (expect) {
+        if (sw) k_fwdbwd<NW, true, true><<<slots, NW * 32, 0, ctx->stream>>>(a);
+        else k_fwdbwd<NW, false, true><<<slots, NW * 32, 0, ctx->stream>>>(a);
+    } else {
+        if (sw) k_fwdbwd<NW, true, false><<<slots, NW * 32, 0, ctx->stream>>>(a);
+        else k_fwdbwd<NW, false, false><<<slots, NW * 32, 0, ctx->stream>>>(a);
+    }
+    CK(cudaGetLastError());
+    return PHMM_OK;
+}
+
+template <int NW>
+int occupancy_fwdbwd(bool sw, bool expect) {
+    int n = 0;
+    if (expect) {
+        if (sw) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fwdbwd<NW, true, true>, NW * 32, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fwdbwd<NW, false, true>, NW * 32, 0);
+    } else {
+        if (sw) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fwdbwd<NW, true, false>, NW * 32, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fwdbwd<NW, false, false>, NW * 32, 0);
+    }
+    return n > 0 ? n : 1;
+}
+
+int64_t budget(phmm_ctx *ctx) {
+    if (ctx->mem_budget > 0) return ctx->mem_budget;
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    return (int64_t)(fr * 0.8);
+}
+
+// Sizes scratch and (re)allocates it.  pair capacities scale with pair_factor.
+int plan_memory(phmm_ctx *ctx) {
+    BatchState &b = ctx->b;
+    const int64_t nreg = (int64_t)b.regions.size();
+    int64_t cells = 0, diags = 0;
+    b.ring_cells = 2; b.dcap = 4; b.bw = 1; b.max_lx = 1; b.max_ly = 1; b.max_nd = 1; b.max_pairs = 1;
+    b.total_pair_cap = 0; b.total_mrun_cap = 0;
+    for (int64_t i = 0; i < nreg; i++) {
+        Region &r = b.regions[i];
+        const RegionGeom &g = b.geom[i];
+        cells += g.cells; diags += g.diagonals;
+        b.ring_cells = std::max<int64_t>(b.ring_cells, g.max_live_cells + g.max_width + 2);
+        b.dcap = std::max<int32_t>(b.dcap, g.max_live_diags + 4);
+        b.bw = std::max<int32_t>(b.bw, g.max_width);
+        b.max_lx = std::max(b.max_lx, r.lx); b.max_ly = std::max(b.max_ly, r.ly);
+        b.max_nd = std::max(b.max_nd, r.lx + r.ly);
+        const int64_t mn = std::min(r.lx, r.ly);
+        int64_t pc = (int64_t)b.pair_factor * mn + 1024;
+        pc = std::min<int64_t>(pc, g.cells);                 // never more pairs than cells
+        if (pc > 0x7fffffff) return fail(ctx, PHMM_E_ARG, "region too large");
+        r.pair_cap = (int32_t)pc; r.pair_off = b.total_pair_cap; b.total_pair_cap += pc;
+        r.mrun_cap = (int32_t)(mn + 1); r.mrun_off = b.total_mrun_cap; b.total_mrun_cap += mn + 1;
+        b.max_pairs = std::max<int32_t>(b.max_pairs, r.pair_cap);
+    }
+    if (b.ring_cells > 0x7ffffff0) return fail(ctx, PHMM_E_ARG, "forward window too large for one region");
+    b.stats.cells = cells; b.stats.diagonals = diags; b.stats.n_regions = nreg; b.stats.n_reads = b.n_reads;
+    // width class -> warps per region
+    const double avgw = diags > 0 ? (double)cells / (double)diags : 1.0;
+    b.nw = avgw <= 40.0 ? 1 : (avgw <= 96.0 ? 2 : 4);
+    const bool sw = ctx->model.has_switch != 0;
+    int occ = b.nw == 1 ? occupancy_fwdbwd<1>(sw, b.expect) : b.nw == 2 ? occupancy_fwdbwd<2>(sw, b.expect) : occupancy_fwdbwd<4>(sw, b.expect);
+    int64_t want = (int64_t)ctx->sm_count * occ;
+    const int64_t slot_bytes = b.ring_cells * NS * 8 + (int64_t)b.dcap * sizeof(DiagRec) + (int64_t)3 * b.bw * NS * 8 + (int64_t)2 * b.bw * 8;
+    // fixed allocations
+    const int64_t fixed = b.total_pair_cap * 12 + b.total_mrun_cap * 12 + nreg * (sizeof(Region) + sizeof(RegionGeom) + 64);
+    const int64_t dec_slot_bytes = (int64_t)(b.max_lx + 1) * 4 + (int64_t)(b.max_ly + 1) * 4 + (int64_t)(b.max_nd + 4) * 8 +
+                                   (int64_t)(b.max_pairs + 1) * 16 + (int64_t)2 * (b.max_lx + 2) * 8 + (int64_t)3 * b.bw * 12;
+    int64_t avail = budget(ctx) - fixed;
+    if (avail < slot_bytes + dec_slot_bytes) return fail(ctx, PHMM_E_NOMEM, "memory budget too small for one region of this batch");
+    int64_t dec_want = (int64_t)ctx->sm_count * 8;
+    dec_want = std::min<int64_t>(dec_want, nreg);
+    dec_want = std::max<int64_t>(1, std::min<int64_t>(dec_want, (avail / 4) / dec_slot_bytes));
+    avail -= dec_want * dec_slot_bytes;
+    want = std::min<int64_t>(want, nreg);
+    want = std::max<int64_t>(1, std::min<int64_t>(want, avail / slot_bytes));
+    b.fb_slots = (int)want; b.dec_slots = (int)dec_want;
+    b.stats.slot_bytes = slot_bytes; b.stats.n_slots = want;
+
+    CK(ctx->d_fring.ensure((size_t)want * b.ring_cells * NS * 8));
+    CK(ctx->d_dtab.ensure((size_t)want * b.dcap * sizeof(DiagRec)));
+    CK(ctx->d_bring.ensure((size_t)want * 3 * b.bw * NS * 8));
+    CK(ctx->d_dots.ensure((size_t)want * 2 * b.bw * 8));
+    CK(ctx->d_px.ensure((size_t)b.total_pair_cap * 4 + 16));
+    CK(ctx->d_py.ensure((size_t)b.total_pair_cap * 4 + 16));
+    CK(ctx->d_pw.ensure((size_t)b.total_pair_cap * 4 + 16));
+    CK(ctx->d_npairs.ensure((size_t)nreg * 4 + 16));
+    if (b.expect) {
+        CK(ctx->d_expT.ensure((size_t)nreg * 25 * 8));
+        CK(ctx->d_expE.ensure((size_t)nreg * 80 * 8));
+        CK(ctx->d_expLL.ensure((size_t)nreg * 8));
+    } else {
+        CK(ctx->d_sumx.ensure((size_t)dec_want * (b.max_lx + 1) * 4));
+        CK(ctx->d_sumy.ensure((size_t)dec_want * (b.max_ly + 1) * 4));
+        CK(ctx->d_dstart.ensure((size_t)dec_want * (b.max_nd + 4) * 4));
+        CK(ctx->d_dfill.ensure((size_t)dec_want * (b.max_nd + 4) * 4));
+        CK(ctx->d_sidx.ensure((size_t)dec_want * (b.max_pairs + 1) * 4));
+        CK(ctx->d_wre.ensure((size_t)dec_want * (b.max_pairs + 1) * 8));
+        CK(ctx->d_pred.ensure((size_t)dec_want * (b.max_pairs + 1) * 4));
+        CK(ctx->d_colmap.ensure((size_t)dec_want * 2 * (b.max_lx + 2) * 8));
+        CK(ctx->d_sring.ensure((size_t)dec_want * 3 * b.bw * 8));
+        CK(ctx->d_lring.ensure((size_t)dec_want * 3 * b.bw * 4));
+        CK(ctx->d_mrx.ensure((size_t)b.total_mrun_cap * 4 + 16));
+        CK(ctx->d_mry.ensure((size_t)b.total_mrun_cap * 4 + 16));
+        CK(ctx->d_mrn.ensure((size_t)b.total_mrun_cap * 4 + 16));
+        CK(ctx->d_nmruns.ensure((size_t)nreg * 4 + 16));
+        CK(ctx->d_score.ensure((size_t)nreg * 8 + 16));
+    }
+    // regions carry the plan (pair_off, caps): upload
+    CK(cudaMemcpyAsync(ctx->d_regions.p, b.regions.data(), nreg * sizeof(Region), cudaMemcpyHostToDevice, ctx->stream));
+    return PHMM_OK;
+}
+
+int do_prepare(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const int64_t *read_off,
+               const int64_t *ref_start, const int64_t *ref_end, const uint32_t *in_ops, const int64_t *in_off,
+               const phmm_params *params, bool expect) {
+    BatchState &b = ctx->b;
+    b.prepared = false; b.ran = false; b.expect = expect;
+    int rc = check_params(ctx, params);
+    if (rc) return rc;
+    if (ctx->ref_len < 0) return fail(ctx, PHMM_E_STATE, "phmm_set_reference has not been called");
+    if (n_reads < 0) return fail(ctx, PHMM_E_ARG, "n_reads < 0");
+    if (n_reads > 0 && (!read_off || !ref_start || !ref_end || !in_off)) return fail(ctx, PHMM_E_ARG, "NULL input array");
+    CK(cudaSetDevice(ctx->device));
+    b.params = *params;
+    b.n_reads = n_reads;
+    b.pair_factor = 8;
+    memset(&b.stats, 0, sizeof(b.stats));
+    b.regions.clear(); b.runs.clear(); b.geom.clear(); b.order.clear();
+    b.read_first_region.assign(n_reads + 1, 0);
+    b.read_lx.assign(n_reads, 0); b.read_ly.assign(n_reads, 0);
+    for (int64_t i = 0; i < n_reads; i++) {
+        const int64_t lY = read_off[i + 1] - read_off[i];
+        const int64_t lX = ref_end[i] - ref_start[i];
+        if (lY < 0 || lX < 0 || ref_start[i] < 0 || ref_end[i] > ctx->ref_len)
+            return fail(ctx, PHMM_E_ARG, "read " + std::to_string(i) + ": coordinates outside the reference or negative length");
+        b.read_first_region[i] = (int64_t)b.regions.size();
+        b.read_lx[i] = lX; b.read_ly[i] = lY;
+        rc = plan_read(ctx, i, in_ops + in_off[i], in_off[i + 1] - in_off[i], lX, lY, ref_start[i], read_off[i], *params, b.regions, b.runs);
+        if (rc) return rc;
+    }
+    b.read_first_region[n_reads] = (int64_t)b.regions.size();
+    const int64_t nreg = (int64_t)b.regions.size();
+    if (nreg > 0x7ffffff0) return fail(ctx, PHMM_E_ARG, "too many regions in one batch");
+    b.dp.expansion = params->band; b.dp.min_diags = params->min_diags; b.dp.tb_diags = params->tb_diags; b.dp.pad = 0;
+    b.dp.threshold = params->threshold;
+    b.dp.lp_skip = params->threshold > 0.0 ? log(params->threshold) - 1e-3 : -INFINITY;
+    b.dp.gap_gamma = params->gap_gamma; b.dp.match_gamma = params->match_gamma;
+    if (nreg == 0) { b.prepared = true; return PHMM_OK; }
+
+    const int64_t total_read = n_reads ? read_off[n_reads] : 0;
+    CK(ctx->d_reads.ensure((size_t)total_read + 16));
+    CK(ctx->d_regions.ensure((size_t)nreg * sizeof(Region)));
+    CK(ctx->d_runs.ensure((size_t)(b.runs.size() + 1) * sizeof(Run)));
+    CK(ctx->d_geom.ensure((size_t)nreg * sizeof(RegionGeom)));
+    CK(ctx->d_order.ensure((size_t)nreg * 4));
+    CK(ctx->d_counter.ensure(64));
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (total_read) CK(cudaMemcpyAsync(ctx->d_reads.p, read_bases, (size_t)total_read, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_regions.p, b.regions.data(), nreg * sizeof(Region), cudaMemcpyHostToDevice, ctx->stream));
+    if (!b.runs.empty()) CK(cudaMemcpyAsync(ctx->d_runs.p, b.runs.data(), b.runs.size() * sizeof(Run), cudaMemcpyHostToDevice, ctx->stream));
+    k_geometry<<<(unsigned)((nreg + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_regions.as<Region>(), ctx->d_runs.as<Run>(), (int)nreg, b.dp,
+                                                                         ctx->d_geom.as<RegionGeom>());
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    b.geom.resize(nreg);
+    CK(cudaMemcpyAsync(b.geom.data(), ctx->d_geom.p, nreg * sizeof(RegionGeom), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    b.stats.ms_geometry = ms;
+    // longest regions first
+    b.order.resize(nreg);
+    std::iota(b.order.begin(), b.order.end(), 0);
+    std::stable_sort(b.order.begin(), b.order.end(), [&](int32_t x, int32_t y) { return b.geom[x].cells > b.geom[y].cells; });
+    CK(cudaMemcpyAsync(ctx->d_order.p, b.order.data(), nreg * 4, cudaMemcpyHostToDevice, ctx->stream));
+    rc = plan_memory(ctx);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    b.prepared = true;
+    return PHMM_OK;
+}
+
+int do_run(phmm_ctx *ctx) {
+    BatchState &b = ctx->b;
+    if (!b.prepared) return fail(ctx, PHMM_E_STATE, "no batch prepared");
+    const int64_t nreg = (int64_t)b.regions.size();
+    b.stats.launches = 1;   // geometry
+    if (nreg == 0) { b.ran = true; return PHMM_OK; }
+    CK(cudaSetDevice(ctx->device));
+    FbArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.ref = ctx->d_ref.as<uint8_t>(); fa.reads = ctx->d_reads.as<uint8_t>();
+    fa.regions = ctx->d_regions.as<Region>(); fa.runs = ctx->d_runs.as<Run>(); fa.order = ctx->d_order.as<int32_t>();
+    fa.n_regions = (int32_t)nreg; fa.counter = ctx->d_counter.as<int32_t>();
+    fa.m = ctx->model; fa.p = b.dp;
+    fa.fring = ctx->d_fring.as<double>(); fa.ring_cells = b.ring_cells;
+    fa.dtab = ctx->d_dtab.as<DiagRec>(); fa.dcap = b.dcap;
+    fa.bring = ctx->d_bring.as<double>(); fa.bw = b.bw; fa.dots = ctx->d_dots.as<double>();
+    fa.px = ctx->d_px.as<int32_t>(); fa.py = ctx->d_py.as<int32_t>(); fa.pw = ctx->d_pw.as<int32_t>();
+    fa.npairs = ctx->d_npairs.as<int32_t>();
+    fa.expT = ctx->d_expT.as<unsigned long long>(); fa.expE = ctx->d_expE.as<unsigned long long>(); fa.expLL = ctx->d_expLL.as<double>();
+    CK(cudaMemsetAsync(ctx->d_counter.p, 0, 64, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    int rc = b.nw == 1 ? launch_fwdbwd<1>(ctx, fa, b.fb_slots, b.expect)
+           : b.nw == 2 ? launch_fwdbwd<2>(ctx, fa, b.fb_slots, b.expect)
+                       : launch_fwdbwd<4>(ctx, fa, b.fb_slots, b.expect);
+    if (rc) return rc;
+    b.stats.launches++;
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    if (!b.expect) {
+        DecArgs da;
+        memset(&da, 0, sizeof(da));
+        da.regions = fa.regions; da.runs = fa.runs; da.order = fa.order; da.n_regions = fa.n_regions;
+        da.counter = ctx->d_counter.as<int32_t>() + 8;
+        da.p = b.dp;
+        da.px = fa.px; da.py = fa.py; da.pw = fa.pw; da.npairs = fa.npairs;
+        da.sumx = ctx->d_sumx.as<int32_t>(); da.sumy = ctx->d_sumy.as<int32_t>(); da.max_lx = b.max_lx; da.max_ly = b.max_ly;
+        da.dstart = ctx->d_dstart.as<int32_t>(); da.dfill = ctx->d_dfill.as<int32_t>(); da.max_nd = b.max_nd;
+        da.sidx = ctx->d_sidx.as<int32_t>(); da.wre = ctx->d_wre.as<int64_t>(); da.pred = ctx->d_pred.as<int32_t>(); da.max_pairs = b.max_pairs;
+        da.colmap = ctx->d_colmap.as<int64_t>();
+        da.sring = ctx->d_sring.as<int64_t>(); da.lring = ctx->d_lring.as<int32_t>(); da.bw = b.bw;
+        da.mrx = ctx->d_mrx.as<int32_t>(); da.mry = ctx->d_mry.as<int32_t>(); da.mrn = ctx->d_mrn.as<int32_t>();
+        da.nmruns = ctx->d_nmruns.as<int32_t>(); da.score = ctx->d_score.as<int64_t>();
+        if (b.nw == 1) k_decode<1><<<b.dec_slots, 32, 0, ctx->stream>>>(da);
+        else if (b.nw == 2) k_decode<2><<<b.dec_slots, 64, 0, ctx->stream>>>(da);
+        else k_decode<4><<<b.dec_slots, 128, 0, ctx->stream>>>(da);
+        CK(cudaGetLastError());
+        b.stats.launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float m1 = 0.f, m2 = 0.f;
+    cudaEventElapsedTime(&m1, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&m2, ctx->ev[3], ctx->ev[4]);
+    b.stats.ms_fwdbwd = m1; b.stats.ms_decode = m2; b.stats.ms_total = m1 + m2;
+    b.ran = true;
+    return PHMM_OK;
+}
+
+// Re-runs with larger pair buffers while any region overflowed.  Returns the per-region pair counts.
+int run_until_fits(phmm_ctx *ctx, std::vector<int32_t> &npairs) {
+    BatchState &b = ctx->b;
+    const int64_t nreg = (int64_t)b.regions.size();
+    for (int attempt = 0; attempt < 6; attempt++) {
+        if (!b.ran) { int rc = do_run(ctx); if (rc) return rc; }
+        npairs.resize(nreg);
+        if (nreg) CK(cudaMemcpy(npairs.data(), ctx->d_npairs.p, nreg * 4, cudaMemcpyDeviceToHost));
+        bool over = false;
+        for (int64_t i = 0; i < nreg; i++) if (npairs[i] > b.regions[i].pair_cap) { over = true; break; }
+        if (!over) return PHMM_OK;
+        b.pair_factor *= 4;
+        int rc = plan_memory(ctx);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));
+        b.ran = false;
+    }
+    return fail(ctx, PHMM_E_NOMEM, "posterior pair buffers overflowed repeatedly");
+}
+
+void *xmalloc(size_t n) { return malloc(n ? n : 1); }
+
+}  // namespace
+
+extern "C" {
+
+int phmm_version(void) { return PHMM_VERSION; }
+
+void phmm_default_params(phmm_params *p) {
+    if (!p) return;
+    p->band = 10; p->anchor_trim = 14; p->split_side = 3000; p->min_diags = 1000; p->tb_diags = 40;
+    p->threshold = 0.01; p->gap_gamma = 0.5; p->match_gamma = 0.0;
+}
+
+const char *phmm_create_error(void) { return g_create_error.c_str(); }
+
+phmm_ctx *phmm_create(int device, const double *trans, const double *emis, int model_type) {
+    g_create_error.clear();
+    if ((trans == nullptr) != (emis == nullptr)) { g_create_error = "trans and emis must both be given or both be NULL"; return nullptr; }
+    if (model_type != 0 && model_type != 1) { g_create_error = "model_type must be 0 (fiveState) or 1 (fiveStateAsymmetric)"; return nullptr; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (libphmm_sm100 has no CPU fallback)";
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "device ordinal out of range"; return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        g_create_error = "cudaSetDevice / cudaGetDeviceProperties failed";
+        return nullptr;
+    }
+    if (prop.major != 10) {
+        g_create_error = std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                         "; this library is built for sm_100a only";
+        return nullptr;
+    }
+    phmm_ctx *ctx = new phmm_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_error = "cudaStreamCreate failed"; delete ctx; return nullptr;
+    }
+    for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    build_model(ctx->model, trans, emis);
+    return ctx;
+}
+
+void phmm_destroy(phmm_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *phmm_last_error(phmm_ctx *ctx) { return ctx ? ctx->err.c_str() : "NULL ctx"; }
+
+int phmm_set_model(phmm_ctx *ctx, const double *trans, const double *emis, int model_type) {
+    if (!ctx) return PHMM_E_ARG;
+    if ((trans == nullptr) != (emis == nullptr)) return fail(ctx, PHMM_E_ARG, "trans and emis must both be given or both be NULL");
+    if (model_type != 0 && model_type != 1) return fail(ctx, PHMM_E_ARG, "model_type must be 0 or 1");
+    build_model(ctx->model, trans, emis);
+    ctx->b.prepared = false; ctx->b.ran = false;
+    return PHMM_OK;
+}
+
+int phmm_set_reference(phmm_ctx *ctx, const uint8_t *bases, int64_t n) {
+    if (!ctx) return PHMM_E_ARG;
+    if (n < 0 || (n > 0 && !bases)) return fail(ctx, PHMM_E_ARG, "bad reference");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->d_ref.ensure((size_t)n + 16));
+    if (n) CK(cudaMemcpy(ctx->d_ref.p, bases, (size_t)n, cudaMemcpyHostToDevice));
+    ctx->ref_len = n;
+    ctx->b.prepared = false; ctx->b.ran = false;
+    return PHMM_OK;
+}
+
+int phmm_set_memory_budget(phmm_ctx *ctx, int64_t bytes) {
+    if (!ctx) return PHMM_E_ARG;
+    ctx->mem_budget = bytes;
+    return PHMM_OK;
+}
+
+int phmm_batch_prepare(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const int64_t *read_off,
+                       const int64_t *ref_start, const int64_t *ref_end, const uint32_t *in_cigar_ops,
+                       const int64_t *in_cigar_off, const phmm_params *params) {
+    if (!ctx) return PHMM_E_ARG;
+    try {
+        return do_prepare(ctx, n_reads, read_bases, read_off, ref_start, ref_end, in_cigar_ops, in_cigar_off, params, false);
+    } catch (const std::exception &ex) { return fail(ctx, PHMM_E_NOMEM, ex.what()); }
+}
+
+int phmm_batch_run(phmm_ctx *ctx) {
+    if (!ctx) return PHMM_E_ARG;
+    try { return do_run(ctx); } catch (const std::exception &ex) { return fail(ctx, PHMM_E_NOMEM, ex.what()); }
+}
+
+int phmm_batch_get_stats(phmm_ctx *ctx, phmm_batch_stats *out) {
+    if (!ctx || !out) return PHMM_E_ARG;
+    *out = ctx->b.stats;
+    return PHMM_OK;
+}
+
+void phmm_free(void *p) { free(p); }
+
+void phmm_free_posteriors(phmm_posteriors *post) {
+    if (!post) return;
+    free(post->off); free(post->ref_pos); free(post->read_pos); free(post->prob_1e7);
+    memset(post, 0, sizeof(*post));
+}
+
+int phmm_batch_fetch(phmm_ctx *ctx, uint32_t **out_cigar_ops, int64_t **out_cigar_off, phmm_posteriors *post) {
+    if (!ctx) return PHMM_E_ARG;
+    if (!out_cigar_ops || !out_cigar_off) return fail(ctx, PHMM_E_ARG, "NULL output pointer");
+    BatchState &b = ctx->b;
+    if (!b.prepared || b.expect) return fail(ctx, PHMM_E_STATE, "no realignment batch prepared");
+    try {
+        CK(cudaSetDevice(ctx->device));
+        const int64_t nreg = (int64_t)b.regions.size();
+        std::vector<int32_t> npairs;
+        int rc = run_until_fits(ctx, npairs);
+        if (rc) return rc;
+        // match runs: counts -> offsets -> compact -> D2H
+        std::vector<int32_t> nm(nreg);
+        std::vector<int64_t> moff(nreg + 1, 0);
+        std::vector<int32_t> hx, hy, hn;
+        if (nreg) {
+            CK(cudaMemcpy(nm.data(), ctx->d_nmruns.p, nreg * 4, cudaMemcpyDeviceToHost));
+            for (int64_t i = 0; i < nreg; i++) {
+                if (nm[i] > b.regions[i].mrun_cap) return fail(ctx, PHMM_E_CUDA, "match-run buffer overflow (internal)");
+                moff[i + 1] = moff[i] + nm[i];
+            }
+            const int64_t tot = moff[nreg];
+            CK(ctx->d_coff.ensure((size_t)(nreg + 1) * 8));
+            CK(ctx->d_cx.ensure((size_t)tot * 4 + 16)); CK(ctx->d_cy.ensure((size_t)tot * 4 + 16)); CK(ctx->d_cn.ensure((size_t)tot * 4 + 16));
+            CK(cudaMemcpyAsync(ctx->d_coff.p, moff.data(), (nreg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            k_compact<<<(unsigned)nreg, 128, 0, ctx->stream>>>(ctx->d_regions.as<Region>(), ctx->d_nmruns.as<int32_t>(), ctx->d_coff.as<int64_t>(),
+                                                                 (int)nreg, ctx->d_mrx.as<int32_t>(), ctx->d_mry.as<int32_t>(), ctx->d_mrn.as<int32_t>(),
+                                                                 ctx->d_cx.as<int32_t>(), ctx->d_cy.as<int32_t>(), ctx->d_cn.as<int32_t>());
+            CK(cudaGetLastError());
+            b.stats.launches++;
+            hx.resize(tot); hy.resize(tot); hn.resize(tot);
+            if (tot) {
+                CK(cudaMemcpyAsync(hx.data(), ctx->d_cx.p, tot * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(hy.data(), ctx->d_cy.p, tot * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(hn.data(), ctx->d_cn.p, tot * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        // CIGAR assembly: reference-only gap (D) before read-only gap (I) between matched runs
+        std::vector<uint32_t> ops;
+        std::vector<int64_t> off(b.n_reads + 1, 0);
+        auto push = [&](int code, int64_t len, size_t first) {
+            while (len > 0) {
+                if (ops.size() > first && (int)(ops.back() & 3) == code && (ops.back() >> 2) + len <= 0x3fffffff) {
+                    ops.back() = (uint32_t)((((ops.back() >> 2) + len) << 2) | code);
+                    return;
+                }
+                const int64_t l = std::min<int64_t>(len, 0x3fffffff);
+                ops.push_back((uint32_t)((l << 2) | code));
+                len -= l;
+            }
+        };
+        for (int64_t r = 0; r < b.n_reads; r++) {
+            const size_t first = ops.size();
+            int64_t pxx = -1, pyy = -1;
+            for (int64_t g = b.read_first_region[r]; g < b.read_first_region[r + 1]; g++) {
+                const Region &reg = b.regions[g];
+                for (int64_t k = moff[g + 1] - 1; k >= moff[g]; k--) {       // stored in reverse
+                    const int64_t x = reg.x1 + hx[k], y = reg.y1 + hy[k], n = hn[k];
+                    push(2, x - pxx - 1, first);
+                    push(1, y - pyy - 1, first);
+                    push(0, n, first);
+                    pxx = x + n - 1; pyy = y + n - 1;
+                }
+            }
+            push(2, b.read_lx[r] - pxx - 1, first);
+            push(1, b.read_ly[r] - pyy - 1, first);
+            off[r + 1] = (int64_t)ops.size();
+        }
+        *out_cigar_ops = (uint32_t *)xmalloc(ops.size() * 4);
+        *out_cigar_off = (int64_t *)xmalloc(off.size() * 8);
+        if (!*out_cigar_ops || !*out_cigar_off) return fail(ctx, PHMM_E_NOMEM, "host allocation failed");
+        if (!ops.empty()) memcpy(*out_cigar_ops, ops.data(), ops.size() * 4);
+        memcpy(*out_cigar_off, off.data(), off.size() * 8);
+        int64_t tp = 0;
+        for (int64_t i = 0; i < nreg; i++) tp += npairs[i];
+        b.stats.pairs = tp;
+        if (post) {
+            memset(post, 0, sizeof(*post));
+            post->n = tp;
+            post->off = (int64_t *)xmalloc((b.n_reads + 1) * 8);
+            post->ref_pos = (int32_t *)xmalloc(tp * 4); post->read_pos = (int32_t *)xmalloc(tp * 4); post->prob_1e7 = (int32_t *)xmalloc(tp * 4);
+            if (!post->off || !post->ref_pos || !post->read_pos || !post->prob_1e7) return fail(ctx, PHMM_E_NOMEM, "host allocation failed");
+            // compact pairs on the device with the same gather kernel
+            std::vector<int64_t> poff(nreg + 1, 0);
+            for (int64_t i = 0; i < nreg; i++) poff[i + 1] = poff[i] + npairs[i];
+            std::vector<int32_t> qx(tp), qy(tp), qw(tp);
+            if (tp) {
+                // k_compact reads mrun_off/mrun_cap: give it a region table whose mrun fields alias the pair fields
+                std::vector<Region> alias(b.regions);
+                for (auto &g : alias) { g.mrun_off = g.pair_off; g.mrun_cap = g.pair_cap; }
+                DevBuf d_alias;
+                CK(d_alias.ensure(alias.size() * sizeof(Region)));
+                CK(ctx->d_coff.ensure((size_t)(nreg + 1) * 8));
+                CK(ctx->d_cx.ensure((size_t)tp * 4 + 16)); CK(ctx->d_cy.ensure((size_t)tp * 4 + 16)); CK(ctx->d_cn.ensure((size_t)tp * 4 + 16));
+                CK(cudaMemcpyAsync(d_alias.p, alias.data(), alias.size() * sizeof(Region), cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(ctx->d_coff.p, poff.data(), (nreg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+                k_compact<<<(unsigned)nreg, 128, 0, ctx->stream>>>(d_alias.as<Region>(), ctx->d_npairs.as<int32_t>(), ctx->d_coff.as<int64_t>(), (int)nreg,
+                                                                     ctx->d_px.as<int32_t>(), ctx->d_py.as<int32_t>(), ctx->d_pw.as<int32_t>(),
+                                                                     ctx->d_cx.as<int32_t>(), ctx->d_cy.as<int32_t>(), ctx->d_cn.as<int32_t>());
+                CK(cudaGetLastError());
+                b.stats.launches++;
+                CK(cudaMemcpyAsync(qx.data(), ctx->d_cx.p, tp * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(qy.data(), ctx->d_cy.p, tp * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(qw.data(), ctx->d_cn.p, tp * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
+            int64_t o = 0;
+            std::vector<int64_t> idx;
+            for (int64_t r = 0; r < b.n_reads; r++) {
+                post->off[r] = o;
+                const int64_t o0 = o;
+                for (int64_t g = b.read_first_region[r]; g < b.read_first_region[r + 1]; g++) {
+                    const Region &reg = b.regions[g];
+                    for (int64_t k = poff[g]; k < poff[g + 1]; k++) {
+                        post->ref_pos[o] = reg.x1 + qx[k]; post->read_pos[o] = reg.y1 + qy[k]; post->prob_1e7[o] = qw[k];
+                        o++;
+                    }
+                }
+                // canonical order within the read: (ref_pos, read_pos)
+                const int64_t m = o - o0;
+                idx.resize(m);
+                std::iota(idx.begin(), idx.end(), 0);
+                std::sort(idx.begin(), idx.end(), [&](int64_t i, int64_t j) {
+                    if (post->ref_pos[o0 + i] != post->ref_pos[o0 + j]) return post->ref_pos[o0 + i] < post->ref_pos[o0 + j];
+                    return post->read_pos[o0 + i] < post->read_pos[o0 + j];
+                });
+                std::vector<int32_t> t0(m), t1(m), t2(m);
+                for (int64_t i = 0; i < m; i++) { t0[i] = post->ref_pos[o0 + idx[i]]; t1[i] = post->read_pos[o0 + idx[i]]; t2[i] = post->prob_1e7[o0 + idx[i]]; }
+                for (int64_t i = 0; i < m; i++) { post->ref_pos[o0 + i] = t0[i]; post->read_pos[o0 + i] = t1[i]; post->prob_1e7[o0 + i] = t2[i]; }
+            }
+            post->off[b.n_reads] = o;
+        }
+        return PHMM_OK;
+    } catch (const std::exception &ex) { return fail(ctx, PHMM_E_NOMEM, ex.what()); }
+}
+
+int phmm_realign_batch(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const int64_t *read_off,
+                       const int64_t *ref_start, const int64_t *ref_end, const uint32_t *in_cigar_ops,
+                       const int64_t *in_cigar_off, const phmm_params *params, uint32_t **out_cigar_ops,
+                       int64_t **out_cigar_off, phmm_posteriors *post) {
+    int rc = phmm_batch_prepare(ctx, n_reads, read_bases, read_off, ref_start, ref_end, in_cigar_ops, in_cigar_off, params);
+    if (rc) return rc;
+    rc = phmm_batch_run(ctx);
+    if (rc) return rc;
+    return phmm_batch_fetch(ctx, out_cigar_ops, out_cigar_off, post);
+}
+
+int phmm_expectations_batch(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const int64_t *read_off,
+                            const int64_t *ref_start, const int64_t *ref_end, const uint32_t *in_cigar_ops,
+                            const int64_t *in_cigar_off, const phmm_params *params, double out_stats[106]) {
+    if (!ctx) return PHMM_E_ARG;
+    if (!out_stats) return fail(ctx, PHMM_E_ARG, "out_stats is NULL");
+    try {
+        int rc = do_prepare(ctx, n_reads, read_bases, read_off, ref_start, ref_end, in_cigar_ops, in_cigar_off, params, true);
+        if (rc) return rc;
+        rc = do_run(ctx);
+        if (rc) return rc;
+        BatchState &b = ctx->b;
+        const int64_t nreg = (int64_t)b.regions.size();
+        std::vector<unsigned long long> T(nreg * 25), E(nreg * 80);
+        std::vector<double> LL(nreg);
+        if (nreg) {
+            CK(cudaMemcpy(T.data(), ctx->d_expT.p, nreg * 25 * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(E.data(), ctx->d_expE.p, nreg * 80 * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(LL.data(), ctx->d_expLL.p, nreg * 8, cudaMemcpyDeviceToHost));
+        }
+        for (int k = 0; k < 106; k++) out_stats[k] = 0.0;
+        // fixed order: read by read, region by region -> identical sums for any sharding that keeps read order
+        for (int64_t g = 0; g < nreg; g++) {
+            for (int k = 0; k < 25; k++) out_stats[k] += (double)(int64_t)T[g * 25 + k] / 4294967296.0;
+            for (int k = 0; k < 80; k++) out_stats[25 + k] += (double)(int64_t)E[g * 80 + k] / 4294967296.0;
+            out_stats[105] += LL[g];
+        }
+        return PHMM_OK;
+    } catch (const std::exception &ex) { return fail(ctx, PHMM_E_NOMEM, ex.what()); }
+}
+
+}  // extern "C"

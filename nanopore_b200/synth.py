@@ -1,0 +1,231 @@
+"""Seeded synthetic workloads for the realignment path.
+
+No genomes or nanopore reads are available offline, so the benchmark inputs are
+generated: an i.i.d. ACGT reference, reads drawn from a window of it through a
+substitution/insertion/deletion channel, and the guide alignment a mapper would
+hand to the realigner in the chained-global form `mergeChainedAlignedReads`
+emits (reference nanopore/analyses/utils.py:344-346,366-382: pos = 0, leading
+`D` up to the window start, trailing `D` to the reference end).
+
+The error channel follows the spirit of the reference's own
+`mutateSequence` (nanopore/analyses/mutate_reference.py:11-12), extended with
+indels.
+"""
+import numpy as np
+
+BASES = np.frombuffer(b"ACGTN", dtype=np.uint8)
+_CODE = np.full(256, 4, dtype=np.uint8)
+for _i, _c in enumerate(b"ACGT"):
+    _CODE[_c] = _i
+    _CODE[ord(chr(_c).lower())] = _i
+
+OP_M, OP_I, OP_D = 0, 1, 2
+
+
+def encode(seq):
+    """str/bytes -> uint8 codes A=0 C=1 G=2 T=3 other=4."""
+    if isinstance(seq, str):
+        seq = seq.encode("ascii")
+    return _CODE[np.frombuffer(seq, dtype=np.uint8)]
+
+
+def decode(codes):
+    return BASES[np.asarray(codes, dtype=np.uint8)].tobytes().decode("ascii")
+
+
+def reverse_complement_codes(codes):
+    c = np.asarray(codes, dtype=np.uint8)[::-1].copy()
+    m = c < 4
+    c[m] = 3 - c[m]
+    return c
+
+
+def pack_ops(ops):
+    """[(code, length), ...] -> uint32 (length<<2)|code, merging neighbours of equal code."""
+    out = []
+    for code, ln in ops:
+        if ln <= 0:
+            continue
+        if out and out[-1][0] == code:
+            out[-1][1] += ln
+        else:
+            out.append([code, ln])
+    return np.array([(ln << 2) | code for code, ln in out], dtype=np.uint32)
+
+
+def unpack_ops(packed):
+    return [(int(v) & 3, int(v) >> 2) for v in np.asarray(packed)]
+
+
+def random_reference(length, rng):
+    return rng.integers(0, 4, size=length, dtype=np.uint8)
+
+
+def _rle(ops):
+    """uint8 op stream -> packed uint32 runs."""
+    if len(ops) == 0:
+        return np.zeros(0, dtype=np.uint32)
+    cut = np.flatnonzero(np.diff(ops)) + 1
+    starts = np.concatenate(([0], cut))
+    ends = np.concatenate((cut, [len(ops)]))
+    return ((ends - starts).astype(np.uint32) << 2) | ops[starts].astype(np.uint32)
+
+
+def simulate_read(ref, start, length, rng, sub=0.05, ins=0.04, dele=0.06, geo_p=0.6, min_match_run=8):
+    """One read from ref[start:start+length].
+
+    Returns (read codes, local guide ops packed) where the ops describe the true
+    edit script degraded the way a seed-and-extend mapper would report it:
+    matched runs shorter than `min_match_run` are folded into the neighbouring
+    indels.  Ops span exactly `length` reference bases and
+    len(read) read bases.
+    """
+    w = ref[start:start + length]
+    n = len(w)
+    # deletions: runs of reference bases dropped
+    dstart = rng.random(n) < dele
+    dlen = rng.geometric(geo_p, size=n)
+    mark = np.zeros(n + 1, dtype=np.int64)
+    idx = np.flatnonzero(dstart)
+    np.add.at(mark, idx, 1)
+    np.add.at(mark, np.minimum(idx + dlen[idx], n), -1)
+    deleted = np.cumsum(mark[:n]) > 0
+    # never delete the first/last base of the window: keeps the local script anchored
+    deleted[0] = deleted[-1] = False
+    # insertions before kept positions
+    ilen = np.where(rng.random(n) < ins, rng.geometric(geo_p, size=n), 0)
+    ilen[0] = 0
+    ilen[deleted] = 0
+    # column stream: for each reference position: ilen[i] I-columns then one M or D column
+    cols_per = ilen + 1
+    total = int(cols_per.sum())
+    ops = np.full(total, OP_I, dtype=np.uint8)
+    last = np.cumsum(cols_per) - 1
+    ops[last] = np.where(deleted, OP_D, OP_M)
+    # read bases
+    kept = ~deleted
+    bases = w.copy()
+    smask = (rng.random(n) < sub) & kept
+    bases[smask] = (bases[smask] + rng.integers(1, 4, size=int(smask.sum()), dtype=np.uint8)) % 4
+    read = np.empty(int(ilen.sum() + kept.sum()), dtype=np.uint8)
+    is_read_col = ops != OP_D
+    col_is_m = ops == OP_M
+    read_cols = np.flatnonzero(is_read_col)
+    m_in_read = col_is_m[read_cols]
+    read[m_in_read] = bases[kept]
+    read[~m_in_read] = rng.integers(0, 4, size=int((~m_in_read).sum()), dtype=np.uint8)
+    runs = _rle(ops)
+    if min_match_run > 1:
+        # fold short matched runs into indels: M(k) -> D(k) I(k)
+        folded = []
+        for v in runs:
+            code, ln = int(v) & 3, int(v) >> 2
+            if code == OP_M and ln < min_match_run:
+                folded.append((OP_D, ln))
+                folded.append((OP_I, ln))
+            else:
+                folded.append((code, ln))
+        # canonicalise each gap block between M runs as D then I
+        canon, d_acc, i_acc = [], 0, 0
+        for code, ln in folded:
+            if code == OP_M:
+                if d_acc:
+                    canon.append((OP_D, d_acc))
+                if i_acc:
+                    canon.append((OP_I, i_acc))
+                d_acc = i_acc = 0
+                canon.append((OP_M, ln))
+            elif code == OP_D:
+                d_acc += ln
+            else:
+                i_acc += ln
+        if d_acc:
+            canon.append((OP_D, d_acc))
+        if i_acc:
+            canon.append((OP_I, i_acc))
+        runs = pack_ops(canon)
+    return read, runs
+
+
+def globalise(local_ops, start, length, ref_len):
+    """Chained-global form (utils.py:344-346,366-382): leading/trailing D to span the reference."""
+    ops = [(OP_D, start)] + unpack_ops(local_ops) + [(OP_D, ref_len - start - length)]
+    return pack_ops(ops)
+
+
+class Batch:
+    """Packed batch in the layout of include/phmm.h."""
+
+    def __init__(self, ref, reads, read_off, ref_start, ref_end, in_ops, in_off, names=None, reverse=None):
+        self.ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        self.reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        self.read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+        self.ref_start = np.ascontiguousarray(ref_start, dtype=np.int64)
+        self.ref_end = np.ascontiguousarray(ref_end, dtype=np.int64)
+        self.in_ops = np.ascontiguousarray(in_ops, dtype=np.uint32)
+        self.in_off = np.ascontiguousarray(in_off, dtype=np.int64)
+        self.names = names
+        self.reverse = reverse
+
+    @property
+    def n(self):
+        return len(self.read_off) - 1
+
+    def read(self, i):
+        return self.reads[self.read_off[i]:self.read_off[i + 1]]
+
+    def ops(self, i):
+        return self.in_ops[self.in_off[i]:self.in_off[i + 1]]
+
+    def subset(self, idx):
+        idx = np.asarray(idx, dtype=np.int64)
+        reads = [self.read(i) for i in idx]
+        ops = [self.ops(i) for i in idx]
+        return Batch(self.ref,
+                     np.concatenate(reads) if reads else np.zeros(0, np.uint8),
+                     np.concatenate(([0], np.cumsum([len(r) for r in reads]))).astype(np.int64),
+                     self.ref_start[idx], self.ref_end[idx],
+                     np.concatenate(ops) if ops else np.zeros(0, np.uint32),
+                     np.concatenate(([0], np.cumsum([len(o) for o in ops]))).astype(np.int64),
+                     [self.names[i] for i in idx] if self.names else None,
+                     self.reverse[idx] if self.reverse is not None else None)
+
+
+def make_batch(n_reads, read_len, ref_len, seed, sub=0.05, ins=0.04, dele=0.06, global_form=True,
+               min_match_run=8, lengths=None):
+    """n_reads reads of ~read_len reference bases each from one random reference.
+
+    lengths: optional per-read reference-window lengths (mixed-length config).
+    With global_form the guide alignment spans the whole reference the way the
+    chaining step hands it to the realigner; otherwise ref_start/ref_end are
+    the read's own window.
+    """
+    rng = np.random.default_rng(seed)
+    ref = random_reference(ref_len, rng)
+    reads, ops, rs, re_, names, rev = [], [], [], [], [], []
+    for i in range(n_reads):
+        ln = int(lengths[i]) if lengths is not None else read_len
+        ln = min(ln, ref_len)
+        start = int(rng.integers(0, ref_len - ln + 1))
+        r, o = simulate_read(ref, start, ln, rng, sub, ins, dele, min_match_run=min_match_run)
+        if global_form:
+            o = globalise(o, start, ln, ref_len)
+            rs.append(0)
+            re_.append(ref_len)
+        else:
+            rs.append(start)
+            re_.append(start + ln)
+        reads.append(r)
+        ops.append(o)
+        names.append("read_%d" % i)
+        rev.append(bool(rng.random() < 0.5))
+    read_off = np.concatenate(([0], np.cumsum([len(r) for r in reads]))).astype(np.int64)
+    in_off = np.concatenate(([0], np.cumsum([len(o) for o in ops]))).astype(np.int64)
+    return Batch(ref, np.concatenate(reads), read_off, rs, re_, np.concatenate(ops), in_off, names,
+                 np.array(rev, dtype=bool))
+
+
+def pareto_lengths(n, seed, lo=500, hi=50000, alpha=1.2):
+    """Mixed-length config: clip(lo * Pareto(alpha), lo, hi)."""
+    rng = np.random.default_rng(seed)
+    return np.clip(lo * (1.0 + rng.pareto(alpha, size=n)), lo, hi).astype(np.int64)

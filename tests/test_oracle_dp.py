@@ -1,0 +1,265 @@
+"""The CPU oracle against independent restatements (no GPU).
+
+The oracle (oracle/phmm_oracle.c) is a restatement of the cPecan algorithm whose
+upstream sources are absent (parity unpinned).  These tests pin its structure
+from the outside: an unbanded exact log-space pair-HMM in numpy, a closed form
+of the band, and a brute-force optimum of the decode objective.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from nanopore_b200 import synth
+
+NEG = -np.inf
+
+
+def lse(a, b):
+    if a == NEG:
+        return b
+    if b == NEG:
+        return a
+    m = max(a, b)
+    return m + math.log1p(math.exp(-abs(a - b)))
+
+
+def model_tables(model):
+    d = model.dump()
+    return d[:25].reshape(5, 5), d[25:50].reshape(5, 5), d[50:55], d[55:60]
+
+
+def brute_force_posteriors(model, X, Y):
+    """Full-matrix forward/backward with exact log-sum-exp (independent of the oracle's code)."""
+    tr, eM, eX, eY = model_tables(model)
+    lx, ly = len(X), len(Y)
+    F = np.full((lx + 1, ly + 1, 5), NEG)
+    F[0, 0, 0] = 0.0
+    for x in range(lx + 1):
+        for y in range(ly + 1):
+            if x == 0 and y == 0:
+                continue
+            if x > 0:
+                for to in (1, 3):
+                    acc = NEG
+                    for fr in (0, 1, 2, 3, 4):
+                        if tr[fr, to] > NEG and F[x - 1, y, fr] > NEG:
+                            acc = lse(acc, F[x - 1, y, fr] + tr[fr, to] + eX[X[x - 1]])
+                    F[x, y, to] = acc
+            if y > 0:
+                for to in (2, 4):
+                    acc = NEG
+                    for fr in (0, 1, 2, 3, 4):
+                        if tr[fr, to] > NEG and F[x, y - 1, fr] > NEG:
+                            acc = lse(acc, F[x, y - 1, fr] + tr[fr, to] + eY[Y[y - 1]])
+                    F[x, y, to] = acc
+            if x > 0 and y > 0:
+                acc = NEG
+                for fr in range(5):
+                    if F[x - 1, y - 1, fr] > NEG:
+                        acc = lse(acc, F[x - 1, y - 1, fr] + tr[fr, 0] + eM[X[x - 1], Y[y - 1]])
+                F[x, y, 0] = acc
+    B = np.full((lx + 1, ly + 1, 5), NEG)
+    B[lx, ly, :] = tr[:, 0]                       # end state: like going to a match
+    for x in range(lx, -1, -1):
+        for y in range(ly, -1, -1):
+            if x == lx and y == ly:
+                continue
+            for fr in range(5):
+                acc = NEG
+                if x < lx and y < ly and B[x + 1, y + 1, 0] > NEG:
+                    acc = lse(acc, B[x + 1, y + 1, 0] + tr[fr, 0] + eM[X[x], Y[y]])
+                if x < lx:
+                    for to in (1, 3):
+                        if tr[fr, to] > NEG and B[x + 1, y, to] > NEG:
+                            acc = lse(acc, B[x + 1, y, to] + tr[fr, to] + eX[X[x]])
+                if y < ly:
+                    for to in (2, 4):
+                        if tr[fr, to] > NEG and B[x, y + 1, to] > NEG:
+                            acc = lse(acc, B[x, y + 1, to] + tr[fr, to] + eY[Y[y]])
+                B[x, y, fr] = acc
+    total = NEG
+    for s in range(5):
+        total = lse(total, F[lx, ly, s] + tr[s, 0])
+    assert abs(B[0, 0, 0] - total) < 1e-8        # forward total == backward total
+    P = np.exp(F[1:, 1:, 0] + B[1:, 1:, 0] - total)
+    return P, total
+
+
+def test_logadd_properties():
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        a, b = rng.uniform(-30, 0, 2)
+        v = oracle.logadd(a, b)
+        assert v == oracle.logadd(b, a)
+        assert abs(v - lse(a, b)) < 6e-4          # cubic fit + cut-off at 7.5 (log1p(exp(-7.5)) = 5.5e-4)
+        assert v >= max(a, b)
+    assert oracle.logadd(NEG, -3.0) == -3.0
+    assert oracle.logadd(-3.0, NEG) == -3.0
+    assert oracle.logadd(NEG, NEG) == NEG
+    assert oracle.logadd(-1.0, -8.5) == -1.0      # |d| >= 7.5 returns the larger operand
+    assert oracle.logadd(-1.0, -8.4999) != -1.0
+
+
+def test_exp_matches_libm():
+    xs = np.concatenate([np.linspace(-40, 2, 5001), np.array([-4.605170185988091, 0.0, -1e-9, -699.9])])
+    for x in xs:
+        ref = math.exp(x)
+        assert abs(oracle.exp(x) - ref) <= 4e-16 * ref
+    assert oracle.exp(NEG) == 0.0
+    assert oracle.exp(-800.0) == 0.0 and oracle.exp(-700.0) == 0.0   # flushed: far below any posterior threshold
+
+
+def closed_form_band(ax, ay, lX, lY, e):
+    """Band as rectangles between consecutive anchors (the form the CUDA kernels use)."""
+    anchors = [(0, 0)] + [(x + 1, y + 1) for x, y in zip(ax, ay)] + [(lX, lY)]
+    L = np.zeros(lX + lY + 1, dtype=np.int64)
+    R = np.zeros(lX + lY + 1, dtype=np.int64)
+    k = 0
+    for d in range(1, lX + lY + 1):
+        (px, py), (nx, ny) = anchors[k], anchors[k + 1]
+        clamp = lambda v, hi: min(max(v, 0), hi)
+        xL, yL = clamp(px - e // 2, lX), clamp(ny + e // 2, lY)
+        xU, yU = clamp(nx + e // 2, lX), clamp(py - e // 2, lY)
+        xlo, xhi = max(xL, d - yL), min(xU, d - yU)
+        L[d], R[d] = 2 * xlo - d, 2 * xhi - d
+        if d == nx + ny and k + 2 < len(anchors):
+            k += 1
+    return L, R
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_band_closed_form(seed):
+    rng = np.random.default_rng(seed)
+    lX, lY = int(rng.integers(20, 300)), int(rng.integers(20, 300))
+    n = int(rng.integers(0, min(lX, lY) // 3))
+    xs = np.sort(rng.choice(lX, size=n, replace=False))
+    ys = np.sort(rng.choice(lY, size=n, replace=False))
+    e = int(rng.choice([0, 2, 10, 50]))
+    L, R = oracle.band(xs, ys, lX, lY, e)
+    L2, R2 = closed_form_band(xs, ys, lX, lY, e)
+    assert (L == L2).all() and (R == R2).all()
+    # every diagonal non-empty, parity right, anchors inside
+    d = np.arange(lX + lY + 1)
+    assert (L <= R).all() and ((L + d) % 2 == 0).all() and ((R + d) % 2 == 0).all()
+    for x, y in zip(xs, ys):
+        dd = x + y + 2
+        assert L[dd] <= x - y <= R[dd]
+
+
+@pytest.mark.parametrize("seed,stock", [(1, True), (2, True), (3, False), (4, False)])
+def test_posteriors_match_unbanded_exact_dp(seed, stock, golden_dir):
+    rng = np.random.default_rng(seed)
+    if stock:
+        model = oracle.Model()
+    else:
+        from nanopore_b200.hmm import Hmm
+        t, e = Hmm.loadHmm(golden_dir + "/blasr_hmm_0.txt").arrays()
+        model = oracle.Model(t, e)
+    lx, ly = int(rng.integers(12, 40)), int(rng.integers(12, 40))
+    X = rng.integers(0, 4, lx).astype(np.uint8)
+    Y = X[:ly].copy() if ly <= lx else np.concatenate([X, rng.integers(0, 4, ly - lx).astype(np.uint8)])
+    flip = rng.random(ly) < 0.15
+    Y[flip] = (Y[flip] + 1) % 4
+    P, total = brute_force_posteriors(model, X, Y)
+    params = oracle.make_params(expansion=2 * (lx + ly + 2), trim=0, threshold=0.0)
+    oracle.set_exact_logadd(True)
+    try:
+        r = oracle.posteriors(model, X, Y, [], [], params)
+    finally:
+        oracle.set_exact_logadd(False)
+    assert len(r["px"]) == lx * ly                # threshold 0 and a full band: every cell reported
+    got = np.zeros((lx, ly))
+    got[r["px"], r["py"]] = r["pw"] / 1e7
+    assert np.abs(got - np.minimum(P, 1.0)).max() < 2e-7      # quantisation 1e-7 + rounding
+    # approximate logAdd stays close to the exact answer
+    r2 = oracle.posteriors(model, X, Y, [], [], params)
+    got2 = np.zeros((lx, ly))
+    got2[r2["px"], r2["py"]] = r2["pw"] / 1e7
+    assert np.abs(got2 - np.minimum(P, 1.0)).max() < 5e-3
+
+
+def brute_chain(px, py, w):
+    order = np.lexsort((py, px))
+    best = np.zeros(len(order), dtype=np.int64)
+    for a, i in enumerate(order):
+        b = 0
+        for c in range(a):
+            j = order[c]
+            if px[j] < px[i] and py[j] < py[i] and best[c] > b:
+                b = best[c]
+        best[a] = b + w[i] if w[i] > 0 else -1
+    return int(max(0, best.max())) if len(best) else 0
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_realign_invariants_and_mea_optimum(seed):
+    b = synth.make_batch(3, 400, 1200, seed=seed)
+    model = oracle.Model()
+    params = oracle.make_params(expansion=10)
+    for i in range(b.n):
+        X = b.ref[b.ref_start[i]:b.ref_end[i]]
+        Y = b.read(i)
+        r = oracle.realign(model, X, Y, b.ops(i), params)
+        ops = synth.unpack_ops(r["ops"])
+        assert sum(l for c, l in ops if c in (0, 2)) == len(X)
+        assert sum(l for c, l in ops if c in (0, 1)) == len(Y)
+        assert all(ops[k][0] != ops[k + 1][0] for k in range(len(ops) - 1))
+        # posterior mass per position <= 1 (+ slack of the approximate logAdd)
+        sx = np.bincount(r["px"], weights=r["pw"], minlength=len(X))
+        sy = np.bincount(r["py"], weights=r["pw"], minlength=len(Y))
+        assert sx.max() <= 1.3e7 and sy.max() <= 1.3e7   # windows and the cubic logAdd leak a little mass
+        assert (r["pw"] >= 1e5).all() and (r["pw"] <= 1e7).all()
+        # chain strictly increasing and made of reported pairs
+        assert (np.diff(r["cx"]) > 0).all() and (np.diff(r["cy"]) > 0).all()
+        pairs = set(zip(r["px"].tolist(), r["py"].tolist()))
+        assert all((x, y) in pairs for x, y in zip(r["cx"].tolist(), r["cy"].tolist()))
+        # decode objective: banded DP score == brute-force optimum over all pairs
+        ipx = np.maximum(0, 10000000 - sx.astype(np.int64))
+        ipy = np.maximum(0, 10000000 - sy.astype(np.int64))
+        wr = r["pw"] - (0.5 * (ipx[r["px"]] + ipy[r["py"]]).astype(np.float64)).astype(np.int64)
+        assert r["mea_score"] == brute_chain(r["px"], r["py"], wr)
+
+
+def test_split_regions():
+    # 200 matched, a 5000 x 40 anchor-free block, 200 matched; side 100 -> block area 200000 > 10000
+    ops = synth.pack_ops([(0, 200), (2, 5000), (1, 40), (0, 200)])
+    lX, lY = 5400, 440
+    reg = oracle.regions(ops, lX, lY, 14, 100)
+    assert len(reg) == 2
+    # last anchor before the block is (185,185); block runs from (186,186) to first anchor after it (5214, 254)
+    x2, y2, x3, y3 = 186, 186, 5200 + 14, 240 + 14
+    hx, hy = min((x3 - x2) // 2, 100), min((y3 - y2) // 2, 100)
+    assert reg[0].tolist()[:4] == [0, 0, x2 + hx, y2 + hy]
+    assert reg[1].tolist()[:4] == [x3 - hx, y3 - hy, lX, lY]
+    assert reg[0][6] == 0 and reg[0][7] == 1 and reg[1][6] == 1 and reg[1][7] == 0
+    # anchors are partitioned between the regions
+    assert reg[0][4] == 0 and reg[0][5] == reg[1][4] == 172 and reg[1][5] == 344
+    # no split when the block is small enough
+    assert len(oracle.regions(ops, lX, lY, 14, 3000)) == 1
+    model = oracle.Model()
+    X = np.random.default_rng(0).integers(0, 4, lX).astype(np.uint8)
+    Y = np.concatenate([X[:200], np.random.default_rng(1).integers(0, 4, 40).astype(np.uint8), X[5200:5400]])
+    r = oracle.realign(model, X, Y, ops, oracle.make_params(expansion=10, split_side=100))
+    out = synth.unpack_ops(r["ops"])
+    assert sum(l for c, l in out if c in (0, 2)) == lX and sum(l for c, l in out if c in (0, 1)) == lY
+    # nothing is aligned inside the skipped middle of the block
+    assert not (((r["px"] >= x2 + hx) & (r["px"] < x3 - hx)).any())
+
+
+def test_expectations_are_a_valid_model():
+    b = synth.make_batch(3, 500, 1500, seed=5)
+    model = oracle.Model()
+    params = oracle.make_params(expansion=10, split_side=300)
+    T, E, ll = np.zeros(25), np.zeros(80), 0.0
+    for i in range(b.n):
+        T, E, ll, _ = oracle.expectations(model, b.ref[b.ref_start[i]:b.ref_end[i]], b.read(i), b.ops(i), params, T, E, ll)
+    T = T.reshape(5, 5)
+    assert (T >= 0).all() and (E >= 0).all() and ll < 0
+    # expected number of emitted read bases ~ read length: match + insert states emit y
+    read_bases = sum(len(b.read(i)) for i in range(b.n))
+    emit_y = T[:, [0, 2, 4]].sum()
+    assert abs(emit_y - read_bases) / read_bases < 0.05
+    # flow conservation: expected entries into a gap state ~ expected exits
+    assert abs(T[0, 1] - T[1, 0]) / max(T[0, 1], 1) < 0.2
