@@ -83,6 +83,9 @@ typedef struct phmm_batch_stats {
     double ms_total;
     int64_t slot_bytes;       /* forward-window scratch per resident thread block */
     int64_t n_slots;
+    int64_t run_launches;     /* kernels launched by the last phmm_batch_run alone */
+    int64_t h2d_bytes;        /* bytes copied host->device by the last prepare */
+    int64_t d2h_bytes;        /* bytes copied device->host by the last prepare + fetch */
 } phmm_batch_stats;
 
 int phmm_version(void);
@@ -99,6 +102,11 @@ phmm_ctx *phmm_create(int device, const double *trans, const double *emis, int m
 const char *phmm_create_error(void);
 void phmm_destroy(phmm_ctx *ctx);
 const char *phmm_last_error(phmm_ctx *ctx);
+
+/* Makes the library launch on the caller's CUDA stream (a cudaStream_t passed as void*; NULL restores
+ * the library's own stream).  New design (the reference has no streams): lets a host that already owns a
+ * stream -- e.g. torch.cuda.current_stream() -- order and time the kernels with its own events. */
+int phmm_set_stream(phmm_ctx *ctx, void *cuda_stream);
 
 /* Swap the HMM (next EM iteration; replaces re-launching with a new --loadHmm). */
 int phmm_set_model(phmm_ctx *ctx, const double *trans, const double *emis, int model_type);

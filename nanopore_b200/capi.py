@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libphmm_sm100.so")
 PHMM_OK = 0
 EXPORTS = [
     "phmm_version", "phmm_default_params", "phmm_create", "phmm_create_error", "phmm_destroy",
-    "phmm_last_error", "phmm_set_model", "phmm_set_reference", "phmm_realign_batch",
+    "phmm_last_error", "phmm_set_stream", "phmm_set_model", "phmm_set_reference", "phmm_realign_batch",
     "phmm_expectations_batch", "phmm_batch_prepare", "phmm_batch_run", "phmm_batch_fetch",
     "phmm_batch_get_stats", "phmm_set_memory_budget", "phmm_free", "phmm_free_posteriors",
 ]
@@ -47,7 +47,8 @@ class BatchStats(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("n_regions", C.c_int64), ("cells", C.c_int64),
                 ("diagonals", C.c_int64), ("pairs", C.c_int64), ("launches", C.c_int64),
                 ("ms_geometry", C.c_double), ("ms_fwdbwd", C.c_double), ("ms_decode", C.c_double),
-                ("ms_total", C.c_double), ("slot_bytes", C.c_int64), ("n_slots", C.c_int64)]
+                ("ms_total", C.c_double), ("slot_bytes", C.c_int64), ("n_slots", C.c_int64),
+                ("run_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -74,6 +75,7 @@ def load_library():
     L.phmm_destroy.argtypes = [vp]
     L.phmm_last_error.restype = C.c_char_p
     L.phmm_last_error.argtypes = [vp]
+    L.phmm_set_stream.argtypes = [vp, vp]
     L.phmm_set_model.argtypes = [vp, vp, vp, i32]
     L.phmm_set_reference.argtypes = [vp, vp, i64]
     batch_in = [vp, i64, vp, vp, vp, vp, vp, vp, C.POINTER(Params)]
@@ -150,6 +152,10 @@ class PhmmContext:
         t, e = self._model_arrays(trans, emis)
         self._check(self._lib.phmm_set_model(self._h, _ptr(t) if t is not None else None,
                                              _ptr(e) if e is not None else None, int(model_type)))
+
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer handle of a cudaStream_t (e.g. torch.cuda.Stream().cuda_stream); 0/None = own stream."""
+        self._check(self._lib.phmm_set_stream(self._h, C.c_void_p(int(cuda_stream or 0))))
 
     def set_reference(self, codes):
         ref = np.ascontiguousarray(codes, dtype=np.uint8)

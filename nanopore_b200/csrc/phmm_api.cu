@@ -65,6 +65,7 @@ struct phmm_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     DevModel model;
@@ -390,6 +391,8 @@ int do_prepare(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const 
                                                                          ctx->d_geom.as<RegionGeom>());
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    b.stats.h2d_bytes = total_read + nreg * (int64_t)sizeof(Region) * 2 + (int64_t)(b.runs.size() * sizeof(Run)) + nreg * 4;
+    b.stats.d2h_bytes = nreg * (int64_t)sizeof(RegionGeom);
     b.geom.resize(nreg);
     CK(cudaMemcpyAsync(b.geom.data(), ctx->d_geom.p, nreg * sizeof(RegionGeom), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -413,6 +416,7 @@ int do_run(phmm_ctx *ctx) {
     if (!b.prepared) return fail(ctx, PHMM_E_STATE, "no batch prepared");
     const int64_t nreg = (int64_t)b.regions.size();
     b.stats.launches = 1;   // geometry
+    b.stats.run_launches = 0;
     if (nreg == 0) { b.ran = true; return PHMM_OK; }
     CK(cudaSetDevice(ctx->device));
     FbArgs fa;
@@ -433,7 +437,7 @@ int do_run(phmm_ctx *ctx) {
            : b.nw == 2 ? launch_fwdbwd<2>(ctx, fa, b.fb_slots, b.expect)
                        : launch_fwdbwd<4>(ctx, fa, b.fb_slots, b.expect);
     if (rc) return rc;
-    b.stats.launches++;
+    b.stats.launches++; b.stats.run_launches++;
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
     if (!b.expect) {
         DecArgs da;
@@ -453,7 +457,7 @@ int do_run(phmm_ctx *ctx) {
         else if (b.nw == 2) k_decode<2><<<b.dec_slots, 64, 0, ctx->stream>>>(da);
         else k_decode<4><<<b.dec_slots, 128, 0, ctx->stream>>>(da);
         CK(cudaGetLastError());
-        b.stats.launches++;
+        b.stats.launches++; b.stats.run_launches++;
     }
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -527,9 +531,10 @@ phmm_ctx *phmm_create(int device, const double *trans, const double *emis, int m
     phmm_ctx *ctx = new phmm_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
         g_create_error = "cudaStreamCreate failed"; delete ctx; return nullptr;
     }
+    ctx->stream = ctx->own_stream;
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     build_model(ctx->model, trans, emis);
     return ctx;
@@ -540,11 +545,19 @@ void phmm_destroy(phmm_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
-    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
 
 const char *phmm_last_error(phmm_ctx *ctx) { return ctx ? ctx->err.c_str() : "NULL ctx"; }
+
+int phmm_set_stream(phmm_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return PHMM_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return PHMM_OK;
+}
 
 int phmm_set_model(phmm_ctx *ctx, const double *trans, const double *emis, int model_type) {
     if (!ctx) return PHMM_E_ARG;
@@ -677,6 +690,7 @@ int phmm_batch_fetch(phmm_ctx *ctx, uint32_t **out_cigar_ops, int64_t **out_ciga
         int64_t tp = 0;
         for (int64_t i = 0; i < nreg; i++) tp += npairs[i];
         b.stats.pairs = tp;
+        b.stats.d2h_bytes = nreg * (int64_t)sizeof(RegionGeom) + nreg * 8 + moff[nreg] * 12 + (post ? tp * 12 : 0);
         if (post) {
             memset(post, 0, sizeof(*post));
             post->n = tp;

@@ -71,6 +71,40 @@ def _rle(ops):
     return ((ends - starts).astype(np.uint32) << 2) | ops[starts].astype(np.uint32)
 
 
+def _fold_short_matches(runs, min_match_run):
+    """Matched runs shorter than min_match_run become D(k) I(k); every gap block between the surviving
+    M runs is then canonicalised as one D followed by one I (vectorised)."""
+    code = (runs & 3).astype(np.int64)
+    ln = (runs >> 2).astype(np.int64)
+    keep_m = (code == OP_M) & (ln >= min_match_run)
+    dl = np.where((code == OP_D) | ((code == OP_M) & ~keep_m), ln, 0)
+    il = np.where((code == OP_I) | ((code == OP_M) & ~keep_m), ln, 0)
+    # gap block g = number of kept M runs before it
+    g = np.cumsum(keep_m) - keep_m
+    nm = int(keep_m.sum())
+    dsum = np.bincount(g[~keep_m], weights=dl[~keep_m], minlength=nm + 1).astype(np.int64)
+    isum = np.bincount(g[~keep_m], weights=il[~keep_m], minlength=nm + 1).astype(np.int64)
+    mlen = ln[keep_m]
+    # interleave: D_0 I_0 M_0 D_1 I_1 M_1 ... D_nm I_nm
+    out_code = np.empty(3 * nm + 2, dtype=np.int64)
+    out_len = np.empty(3 * nm + 2, dtype=np.int64)
+    out_code[0::3] = OP_D
+    out_len[0::3] = dsum
+    out_code[1::3] = OP_I
+    out_len[1::3] = isum
+    out_code[2::3] = OP_M
+    out_len[2::3] = mlen
+    ok = out_len > 0
+    out_code, out_len = out_code[ok], out_len[ok]
+    # merge neighbouring M runs that became adjacent (empty gap block between them)
+    if len(out_code) > 1:
+        first = np.concatenate(([True], out_code[1:] != out_code[:-1]))
+        grp = np.cumsum(first) - 1
+        out_len = np.bincount(grp, weights=out_len).astype(np.int64)
+        out_code = out_code[first]
+    return ((out_len.astype(np.uint32) << 2) | out_code.astype(np.uint32)).astype(np.uint32)
+
+
 def simulate_read(ref, start, length, rng, sub=0.05, ins=0.04, dele=0.06, geo_p=0.6, min_match_run=8):
     """One read from ref[start:start+length].
 
@@ -115,35 +149,8 @@ def simulate_read(ref, start, length, rng, sub=0.05, ins=0.04, dele=0.06, geo_p=
     read[m_in_read] = bases[kept]
     read[~m_in_read] = rng.integers(0, 4, size=int((~m_in_read).sum()), dtype=np.uint8)
     runs = _rle(ops)
-    if min_match_run > 1:
-        # fold short matched runs into indels: M(k) -> D(k) I(k)
-        folded = []
-        for v in runs:
-            code, ln = int(v) & 3, int(v) >> 2
-            if code == OP_M and ln < min_match_run:
-                folded.append((OP_D, ln))
-                folded.append((OP_I, ln))
-            else:
-                folded.append((code, ln))
-        # canonicalise each gap block between M runs as D then I
-        canon, d_acc, i_acc = [], 0, 0
-        for code, ln in folded:
-            if code == OP_M:
-                if d_acc:
-                    canon.append((OP_D, d_acc))
-                if i_acc:
-                    canon.append((OP_I, i_acc))
-                d_acc = i_acc = 0
-                canon.append((OP_M, ln))
-            elif code == OP_D:
-                d_acc += ln
-            else:
-                i_acc += ln
-        if d_acc:
-            canon.append((OP_D, d_acc))
-        if i_acc:
-            canon.append((OP_I, i_acc))
-        runs = pack_ops(canon)
+    if min_match_run > 1 and len(runs):
+        runs = _fold_short_matches(runs, min_match_run)
     return read, runs
 
 
@@ -192,7 +199,7 @@ class Batch:
 
 
 def make_batch(n_reads, read_len, ref_len, seed, sub=0.05, ins=0.04, dele=0.06, global_form=True,
-               min_match_run=8, lengths=None):
+               min_match_run=8, lengths=None, ref=None):
     """n_reads reads of ~read_len reference bases each from one random reference.
 
     lengths: optional per-read reference-window lengths (mixed-length config).
@@ -201,7 +208,11 @@ def make_batch(n_reads, read_len, ref_len, seed, sub=0.05, ins=0.04, dele=0.06, 
     the read's own window.
     """
     rng = np.random.default_rng(seed)
-    ref = random_reference(ref_len, rng)
+    if ref is None:
+        ref = random_reference(ref_len, rng)
+    else:
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        ref_len = len(ref)
     reads, ops, rs, re_, names, rev = [], [], [], [], [], []
     for i in range(n_reads):
         ln = int(lengths[i]) if lengths is not None else read_len
