@@ -162,6 +162,14 @@ int phmm_batch_get_stats(phmm_ctx *ctx, phmm_batch_stats *out);
  * free memory at first use). */
 int phmm_set_memory_budget(phmm_ctx *ctx, int64_t bytes);
 
+/* Tuning / test switches of the library itself (no counterpart in the reference).  Names:
+ *   "legacy_kernel" 1: run the first-generation kernel (forward window wholly in HBM) instead of the
+ *                      windowed shared-memory kernel; results are identical
+ *   "warps"         0 = choose by band width, else 2, 4 or 8 warps per DP region
+ *   "smem_columns"  0 = choose, else the shared-memory diagonal buffer (power of two, 64..1024)
+ * Returns PHMM_E_ARG for an unknown name or value. */
+int phmm_set_option(phmm_ctx *ctx, const char *name, int64_t value);
+
 /* Frees anything returned through an out pointer (ops, offsets, posterior arrays). */
 void phmm_free(void *p);
 void phmm_free_posteriors(phmm_posteriors *post);

@@ -21,7 +21,7 @@ EXPORTS = [
     "phmm_version", "phmm_default_params", "phmm_create", "phmm_create_error", "phmm_destroy",
     "phmm_last_error", "phmm_set_stream", "phmm_set_model", "phmm_set_reference", "phmm_realign_batch",
     "phmm_expectations_batch", "phmm_batch_prepare", "phmm_batch_run", "phmm_batch_fetch",
-    "phmm_batch_get_stats", "phmm_set_memory_budget", "phmm_free", "phmm_free_posteriors",
+    "phmm_batch_get_stats", "phmm_set_memory_budget", "phmm_set_option", "phmm_free", "phmm_free_posteriors",
 ]
 
 
@@ -88,6 +88,7 @@ def load_library():
                                    C.POINTER(Posteriors)]
     L.phmm_batch_get_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.phmm_set_memory_budget.argtypes = [vp, i64]
+    L.phmm_set_option.argtypes = [vp, C.c_char_p, i64]
     L.phmm_free.argtypes = [vp]
     L.phmm_free_posteriors.argtypes = [C.POINTER(Posteriors)]
     _lib = L
@@ -160,6 +161,10 @@ class PhmmContext:
     def set_reference(self, codes):
         ref = np.ascontiguousarray(codes, dtype=np.uint8)
         self._check(self._lib.phmm_set_reference(self._h, _ptr(ref), ref.size))
+
+    def set_option(self, name, value):
+        """Library tuning / test switches, see phmm_set_option in include/phmm.h."""
+        self._check(self._lib.phmm_set_option(self._h, name.encode(), int(value)))
 
     def set_memory_budget(self, nbytes):
         self._check(self._lib.phmm_set_memory_budget(self._h, int(nbytes)))

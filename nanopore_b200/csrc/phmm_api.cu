@@ -15,25 +15,27 @@
 #include <vector>
 
 #include "../../include/phmm.h"
-#include "phmm_kernels.cuh"
+#include "phmm_fb2.cuh"
 
 using namespace phmm;
 
 namespace {
 
 thread_local std::string g_create_error;
+thread_local int64_t g_held_bytes = 0;      // device bytes held by DevBufs of this thread's contexts
 
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { release(); }
+    void release() { if (p) { cudaFree(p); g_held_bytes -= (int64_t)cap; p = nullptr; cap = 0; } }
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        release();
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { (void)cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
-        if (e == cudaSuccess) cap = want; else p = nullptr;
+        if (e == cudaSuccess) { cap = want; g_held_bytes += (int64_t)want; } else p = nullptr;
         return e;
     }
     template <typename T> T *as() { return reinterpret_cast<T *>(p); }
@@ -56,6 +58,11 @@ struct BatchState {
     int32_t max_lx = 0, max_ly = 0, max_nd = 0, max_pairs = 0;
     int64_t total_pair_cap = 0, total_mrun_cap = 0;
     int pair_factor = 8;
+    // windowed kernel (k_fb2)
+    bool fast = false;
+    std::vector<int64_t> tb_off;              // n_regions + 1
+    int64_t ring_doubles = 0; int32_t wcap = 0, wg = 0, tcap = 0;
+    size_t fb2_smem = 0;
     phmm_batch_stats stats;
 };
 
@@ -70,9 +77,12 @@ struct phmm_ctx {
     std::string err;
     DevModel model;
     int64_t mem_budget = 0;
+    bool force_legacy = false;
+    int opt_warps = 0, opt_wcap = 0;             // tests: run the first-generation kernel (k_fwdbwd) instead of k_fb2
     DevBuf d_ref; int64_t ref_len = -1;
     DevBuf d_reads, d_regions, d_runs, d_geom, d_order, d_counter;
     DevBuf d_fring, d_dtab, d_bring, d_dots;
+    DevBuf d_tboff, d_tbp, d_ring, d_wide, d_fsave, d_totals;
     DevBuf d_px, d_py, d_pw, d_npairs;
     DevBuf d_expT, d_expE, d_expLL;
     DevBuf d_sumx, d_sumy, d_dstart, d_dfill, d_sidx, d_wre, d_pred, d_colmap, d_sring, d_lring;
@@ -250,11 +260,34 @@ int occupancy_fwdbwd(bool sw, bool expect) {
     return n > 0 ? n : 1;
 }
 
+template <int NW, bool SW>
+int fb2_occupancy(size_t smem) {
+    int n = 0;
+    if (cudaFuncSetAttribute(k_fb2<NW, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fb2<NW, SW>, NW * 32, smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+int fb2_occupancy(int nw, bool sw, size_t smem) {
+    if (nw == 2) return sw ? fb2_occupancy<2, true>(smem) : fb2_occupancy<2, false>(smem);
+    if (nw == 4) return sw ? fb2_occupancy<4, true>(smem) : fb2_occupancy<4, false>(smem);
+    return sw ? fb2_occupancy<8, true>(smem) : fb2_occupancy<8, false>(smem);
+}
+
+void fb2_launch(int nw, bool sw, const Fb2Args &a, int slots, size_t smem, cudaStream_t st) {
+    if (nw == 2) { if (sw) k_fb2<2, true><<<slots, 64, smem, st>>>(a); else k_fb2<2, false><<<slots, 64, smem, st>>>(a); }
+    else if (nw == 4) { if (sw) k_fb2<4, true><<<slots, 128, smem, st>>>(a); else k_fb2<4, false><<<slots, 128, smem, st>>>(a); }
+    else { if (sw) k_fb2<8, true><<<slots, 256, smem, st>>>(a); else k_fb2<8, false><<<slots, 256, smem, st>>>(a); }
+}
+
+int32_t pow2_at_least(int32_t v) { int32_t p = 1; while (p < v) p <<= 1; return p; }
+
 int64_t budget(phmm_ctx *ctx) {
     if (ctx->mem_budget > 0) return ctx->mem_budget;
     size_t fr = 0, tot = 0;
     cudaMemGetInfo(&fr, &tot);
-    return (int64_t)(fr * 0.8);
+    // what is free now plus what this library already holds and will reuse
+    return (int64_t)(((double)fr + (double)g_held_bytes) * 0.8);
 }
 
 // Sizes scratch and (re)allocates it.  pair capacities scale with pair_factor.
@@ -285,11 +318,31 @@ int plan_memory(phmm_ctx *ctx) {
     b.stats.cells = cells; b.stats.diagonals = diags; b.stats.n_regions = nreg; b.stats.n_reads = b.n_reads;
     // width class -> warps per region
     const double avgw = diags > 0 ? (double)cells / (double)diags : 1.0;
-    b.nw = avgw <= 40.0 ? 1 : (avgw <= 96.0 ? 2 : 4);
     const bool sw = ctx->model.has_switch != 0;
-    int occ = b.nw == 1 ? occupancy_fwdbwd<1>(sw, b.expect) : b.nw == 2 ? occupancy_fwdbwd<2>(sw, b.expect) : occupancy_fwdbwd<4>(sw, b.expect);
+    int64_t max_live_doubles = 0;
+    for (int64_t i = 0; i < nreg; i++) max_live_doubles = std::max(max_live_doubles, b.geom[i].max_live_doubles);
+    // the windowed kernel needs a total-probability schedule that looks one traceback point ahead
+    b.fast = !b.expect && !ctx->force_legacy && b.params.min_diags >= 2 * (b.params.tb_diags + 1) + 2 &&
+             max_live_doubles + 7 * (int64_t)b.bw + 16 < 0x7ffffff0;
+    int occ = 1;
+    int64_t slot_bytes = 0;
+    if (b.fast) {
+        b.nw = ctx->opt_warps ? ctx->opt_warps : (avgw <= 48.0 ? 2 : (avgw <= 112.0 ? 4 : 8));
+        b.wg = pow2_at_least(b.bw);
+        b.wcap = ctx->opt_wcap ? ctx->opt_wcap : std::max<int32_t>(64, std::min<int32_t>(512, b.wg));
+        b.ring_doubles = max_live_doubles + 7 * (int64_t)b.bw + 16;
+        b.tcap = b.dcap / TOTAL_EVERY + 4;
+        b.fb2_smem = (size_t)2 * NS * b.wcap * 8 + 16 * 8 + sizeof(EmisTables) + 16;
+        occ = fb2_occupancy(b.nw, sw, b.fb2_smem);
+        if (occ < 1) return fail(ctx, PHMM_E_CUDA, "k_fb2 does not fit on this device");
+        slot_bytes = b.ring_doubles * 8 + (int64_t)b.dcap * sizeof(DiagRec) + (int64_t)4 * NS * b.wg * 8 +
+                     (int64_t)2 * NS * b.wcap * 8 + (int64_t)b.tcap * 8;
+    } else {
+        b.nw = avgw <= 40.0 ? 1 : (avgw <= 96.0 ? 2 : 4);
+        occ = b.nw == 1 ? occupancy_fwdbwd<1>(sw, b.expect) : b.nw == 2 ? occupancy_fwdbwd<2>(sw, b.expect) : occupancy_fwdbwd<4>(sw, b.expect);
+        slot_bytes = b.ring_cells * NS * 8 + (int64_t)b.dcap * sizeof(DiagRec) + (int64_t)3 * b.bw * NS * 8 + (int64_t)2 * b.bw * 8;
+    }
     int64_t want = (int64_t)ctx->sm_count * occ;
-    const int64_t slot_bytes = b.ring_cells * NS * 8 + (int64_t)b.dcap * sizeof(DiagRec) + (int64_t)3 * b.bw * NS * 8 + (int64_t)2 * b.bw * 8;
     // fixed allocations
     const int64_t fixed = b.total_pair_cap * 12 + b.total_mrun_cap * 12 + nreg * (sizeof(Region) + sizeof(RegionGeom) + 64);
     const int64_t dec_slot_bytes = (int64_t)(b.max_lx + 1) * 4 + (int64_t)(b.max_ly + 1) * 4 + (int64_t)(b.max_nd + 4) * 8 +
@@ -305,10 +358,19 @@ int plan_memory(phmm_ctx *ctx) {
     b.fb_slots = (int)want; b.dec_slots = (int)dec_want;
     b.stats.slot_bytes = slot_bytes; b.stats.n_slots = want;
 
-    CK(ctx->d_fring.ensure((size_t)want * b.ring_cells * NS * 8));
     CK(ctx->d_dtab.ensure((size_t)want * b.dcap * sizeof(DiagRec)));
-    CK(ctx->d_bring.ensure((size_t)want * 3 * b.bw * NS * 8));
-    CK(ctx->d_dots.ensure((size_t)want * 2 * b.bw * 8));
+    if (b.fast) {
+        ctx->d_fring.release(); ctx->d_bring.release(); ctx->d_dots.release();
+        CK(ctx->d_ring.ensure((size_t)want * b.ring_doubles * 8));
+        CK(ctx->d_wide.ensure((size_t)want * 4 * NS * b.wg * 8));
+        CK(ctx->d_fsave.ensure((size_t)want * 2 * NS * b.wcap * 8));
+        CK(ctx->d_totals.ensure((size_t)want * b.tcap * 8));
+    } else {
+        ctx->d_ring.release(); ctx->d_wide.release();
+        CK(ctx->d_fring.ensure((size_t)want * b.ring_cells * NS * 8));
+        CK(ctx->d_bring.ensure((size_t)want * 3 * b.bw * NS * 8));
+        CK(ctx->d_dots.ensure((size_t)want * 2 * b.bw * 8));
+    }
     CK(ctx->d_px.ensure((size_t)b.total_pair_cap * 4 + 16));
     CK(ctx->d_py.ensure((size_t)b.total_pair_cap * 4 + 16));
     CK(ctx->d_pw.ensure((size_t)b.total_pair_cap * 4 + 16));
@@ -383,12 +445,22 @@ int do_prepare(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const 
     CK(ctx->d_geom.ensure((size_t)nreg * sizeof(RegionGeom)));
     CK(ctx->d_order.ensure((size_t)nreg * 4));
     CK(ctx->d_counter.ensure(64));
+    // upper bound of traceback points per region: consecutive points are >= min_diags - tb_diags - 1 apart
+    b.tb_off.assign(nreg + 1, 0);
+    {
+        const int64_t gap = std::max<int64_t>(1, (int64_t)params->min_diags - params->tb_diags - 1);
+        for (int64_t i = 0; i < nreg; i++) b.tb_off[i + 1] = b.tb_off[i] + ((int64_t)b.regions[i].lx + b.regions[i].ly) / gap + 2;
+    }
+    CK(ctx->d_tboff.ensure((size_t)(nreg + 1) * 8));
+    CK(ctx->d_tbp.ensure((size_t)b.tb_off[nreg] * 4 + 16));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tboff.p, b.tb_off.data(), (size_t)(nreg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (total_read) CK(cudaMemcpyAsync(ctx->d_reads.p, read_bases, (size_t)total_read, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_regions.p, b.regions.data(), nreg * sizeof(Region), cudaMemcpyHostToDevice, ctx->stream));
     if (!b.runs.empty()) CK(cudaMemcpyAsync(ctx->d_runs.p, b.runs.data(), b.runs.size() * sizeof(Run), cudaMemcpyHostToDevice, ctx->stream));
     k_geometry<<<(unsigned)((nreg + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_regions.as<Region>(), ctx->d_runs.as<Run>(), (int)nreg, b.dp,
-                                                                         ctx->d_geom.as<RegionGeom>());
+                                                                         ctx->d_geom.as<RegionGeom>(), ctx->d_tboff.as<int64_t>(),
+                                                                         ctx->d_tbp.as<int32_t>());
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     b.stats.h2d_bytes = total_read + nreg * (int64_t)sizeof(Region) * 2 + (int64_t)(b.runs.size() * sizeof(Run)) + nreg * 4;
@@ -433,9 +505,28 @@ int do_run(phmm_ctx *ctx) {
     fa.expT = ctx->d_expT.as<unsigned long long>(); fa.expE = ctx->d_expE.as<unsigned long long>(); fa.expLL = ctx->d_expLL.as<double>();
     CK(cudaMemsetAsync(ctx->d_counter.p, 0, 64, ctx->stream));
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-    int rc = b.nw == 1 ? launch_fwdbwd<1>(ctx, fa, b.fb_slots, b.expect)
+    int rc = PHMM_OK;
+    if (b.fast) {
+        Fb2Args f2;
+        memset(&f2, 0, sizeof(f2));
+        f2.ref = fa.ref; f2.reads = fa.reads; f2.regions = fa.regions; f2.runs = fa.runs; f2.order = fa.order;
+        f2.n_regions = fa.n_regions; f2.counter = fa.counter; f2.m = ctx->model; f2.p = b.dp;
+        f2.tb_off = ctx->d_tboff.as<int64_t>(); f2.tbp = ctx->d_tbp.as<int32_t>();
+        f2.ntb = reinterpret_cast<const int32_t *>(ctx->d_geom.as<char>() + offsetof(RegionGeom, tracebacks));
+        f2.ntb_stride = (int32_t)(sizeof(RegionGeom) / 4);
+        f2.ring = ctx->d_ring.as<double>(); f2.ring_doubles = b.ring_doubles;
+        f2.dtab = ctx->d_dtab.as<DiagRec>(); f2.dcap = b.dcap;
+        f2.wide = ctx->d_wide.as<double>(); f2.wg = b.wg;
+        f2.fsave = ctx->d_fsave.as<double>(); f2.totals = ctx->d_totals.as<double>(); f2.tcap = b.tcap;
+        f2.wcap = b.wcap;
+        f2.px = fa.px; f2.py = fa.py; f2.pw = fa.pw; f2.npairs = fa.npairs;
+        fb2_launch(b.nw, ctx->model.has_switch != 0, f2, b.fb_slots, b.fb2_smem, ctx->stream);
+        CK(cudaGetLastError());
+    } else {
+        rc = b.nw == 1 ? launch_fwdbwd<1>(ctx, fa, b.fb_slots, b.expect)
            : b.nw == 2 ? launch_fwdbwd<2>(ctx, fa, b.fb_slots, b.expect)
                        : launch_fwdbwd<4>(ctx, fa, b.fb_slots, b.expect);
+    }
     if (rc) return rc;
     b.stats.launches++; b.stats.run_launches++;
     CK(cudaEventRecord(ctx->ev[3], ctx->stream));
@@ -455,7 +546,7 @@ int do_run(phmm_ctx *ctx) {
         da.nmruns = ctx->d_nmruns.as<int32_t>(); da.score = ctx->d_score.as<int64_t>();
         if (b.nw == 1) k_decode<1><<<b.dec_slots, 32, 0, ctx->stream>>>(da);
         else if (b.nw == 2) k_decode<2><<<b.dec_slots, 64, 0, ctx->stream>>>(da);
-        else k_decode<4><<<b.dec_slots, 128, 0, ctx->stream>>>(da);
+        else k_decode<4><<<b.dec_slots, 128, 0, ctx->stream>>>(da);          // also for the 8-warp forward/backward class
         CK(cudaGetLastError());
         b.stats.launches++; b.stats.run_launches++;
     }
@@ -575,6 +666,21 @@ int phmm_set_reference(phmm_ctx *ctx, const uint8_t *bases, int64_t n) {
     CK(ctx->d_ref.ensure((size_t)n + 16));
     if (n) CK(cudaMemcpy(ctx->d_ref.p, bases, (size_t)n, cudaMemcpyHostToDevice));
     ctx->ref_len = n;
+    ctx->b.prepared = false; ctx->b.ran = false;
+    return PHMM_OK;
+}
+
+int phmm_set_option(phmm_ctx *ctx, const char *name, int64_t value) {
+    if (!ctx || !name) return PHMM_E_ARG;
+    const std::string n(name);
+    if (n == "legacy_kernel") ctx->force_legacy = value != 0;
+    else if (n == "warps") {
+        if (value != 0 && value != 2 && value != 4 && value != 8) return fail(ctx, PHMM_E_ARG, "warps must be 0, 2, 4 or 8");
+        ctx->opt_warps = (int)value;
+    } else if (n == "smem_columns") {
+        if (value != 0 && (value < 64 || value > 1024 || (value & (value - 1)))) return fail(ctx, PHMM_E_ARG, "smem_columns must be 0 or a power of two in [64, 1024]");
+        ctx->opt_wcap = (int)value;
+    } else return fail(ctx, PHMM_E_ARG, "unknown option " + n);
     ctx->b.prepared = false; ctx->b.ran = false;
     return PHMM_OK;
 }

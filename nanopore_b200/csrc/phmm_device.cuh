@@ -38,6 +38,7 @@ struct RegionGeom {                   // written by the geometry kernel
     int32_t max_live_diags;
     int32_t tracebacks;
     int32_t diagonals;
+    int64_t max_live_doubles;         // peak of the windowed kernel's ring (2 or 7 doubles per cell, see phmm_fb2.cuh)
 };
 
 struct DevModel {                     // log-space stateMachine5
@@ -57,11 +58,15 @@ struct DevParams {
 };
 
 struct DiagRec {                      // one live diagonal of the forward window
-    int32_t off;                      // ring offset in cells
+    int32_t off;                      // ring offset (cells in k_fwdbwd, doubles in k_fb2)
     int32_t xlo;                      // first x of the diagonal
     int32_t w;                        // cells
-    int32_t pad;
+    int32_t pad;                      // k_fb2: 1 = the total probability is evaluated on this diagonal
 };
+
+// Diagonals on which a traceback window evaluates the total probability: every
+// 10th, counted down from the window's first posterior diagonal.
+constexpr int TOTAL_EVERY = 10;
 
 #define PHMM_NEG_INF (__longlong_as_double(0xfff0000000000000LL))
 

@@ -48,14 +48,15 @@ __device__ __forceinline__ void block_sync() {
 // ---------------------------------------------------------------------------
 // geometry: data-independent sweep of the band and of the traceback schedule
 // ---------------------------------------------------------------------------
-__global__ void k_geometry(const Region *regions, const Run *runs, int n_regions, DevParams p, RegionGeom *out) {
+__global__ void k_geometry(const Region *regions, const Run *runs, int n_regions, DevParams p, RegionGeom *out,
+                           const int64_t *tb_off, int32_t *tbp) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_regions) return;
     const Region reg = regions[r];
     RegionGeom g;
     const int nd = reg.lx + reg.ly;
-    g.diagonals = nd + 1;
-    g.cells = 1; g.max_width = 1; g.tracebacks = 0;
+    g.diagonals = nd > 0 ? nd + 1 : 0;              // an empty pair has no DP (the scalar path returns at once)
+    g.cells = nd > 0 ? 1 : 0; g.max_width = 1; g.tracebacks = 0;
     int64_t live = 1, max_live = 1;
     int live_d = 1, max_live_d = 1;
     int wbuf[256];                      // widths of the most recent diagonals (tb_diags + 2 <= 256)
@@ -63,6 +64,8 @@ __global__ void k_geometry(const Region *regions, const Run *runs, int n_regions
     BandIter it;
     it.init(runs + reg.run0, reg.nrun, reg.lx, reg.ly, p.expansion);
     int traced_to = 0;
+    int32_t *tb = tbp + tb_off[r];
+    const int tb_cap = (int)(tb_off[r + 1] - tb_off[r]);
     for (int d = 1; d <= nd; d++) {
         int xlo, w;
         it.diag(d, xlo, w);
@@ -73,8 +76,9 @@ __global__ void k_geometry(const Region *regions, const Run *runs, int n_regions
         if (live > max_live) max_live = live;
         if (live_d > max_live_d) max_live_d = live_d;
         const bool at_end = d == nd;
-        const bool tb = d >= traced_to + p.min_diags && w <= 2 * p.expansion + 1;
-        if (at_end || tb) {
+        const bool tb_here = d >= traced_to + p.min_diags && w <= 2 * p.expansion + 1;
+        if (at_end || tb_here) {
+            if (g.tracebacks < tb_cap) tb[g.tracebacks] = d;
             g.tracebacks++;
             const int traced_from = d - (at_end ? 0 : p.tb_diags + 1);
             // diagonals traced_from..d stay live for the next window
@@ -86,6 +90,36 @@ __global__ void k_geometry(const Region *regions, const Run *runs, int n_regions
     }
     g.max_live_cells = max_live;
     g.max_live_diags = max_live_d;
+    // second sweep: ring usage of the windowed kernel (2 doubles per cell, 7 on total-probability diagonals)
+    g.max_live_doubles = 0;
+    if (nd > 0 && g.tracebacks <= tb_cap) {
+        it.init(runs + reg.run0, reg.nrun, reg.lx, reg.ly, p.expansion);
+        int k = 0;
+        int P = tb[0];
+        int TF = P - (P == nd ? 0 : p.tb_diags + 1);
+        int Pn = g.tracebacks > 1 ? tb[1] : nd;
+        int TFn = Pn - (Pn == nd ? 0 : p.tb_diags + 1);
+        int64_t lv = 0, mx = 0;
+        for (int d = 1; d <= nd; d++) {
+            int xlo, w;
+            it.diag(d, xlo, w);
+            const int tf = d <= TF ? TF : TFn;
+            const bool tot = (tf - d) % TOTAL_EVERY == 0;
+            const int es = w * (tot ? 7 : 2);
+            wbuf[d & 255] = es;
+            lv += es;
+            if (lv > mx) mx = lv;
+            if (d == P) {
+                lv = 0;
+                for (int q = TF + 1; q <= d; q++) lv += wbuf[q & 255];
+                k++;
+                P = Pn; TF = TFn;
+                Pn = k + 1 < g.tracebacks ? tb[k + 1] : nd;
+                TFn = Pn - (Pn == nd ? 0 : p.tb_diags + 1);
+            }
+        }
+        g.max_live_doubles = mx;
+    }
     out[r] = g;
 }
 

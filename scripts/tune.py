@@ -1,0 +1,29 @@
+"""Kernel-only timing of the realignment path under library options (GPU box).
+usage: python scripts/tune.py READS "opt=val,opt=val" ["opt=val" ...]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from nanopore_b200 import capi, synth
+
+n = int(sys.argv[1])
+band = int(os.environ.get("BAND", "50"))
+L, R = int(os.environ.get("READ_LEN", "10000")), int(os.environ.get("REF_LEN", "50000"))
+gf = os.environ.get("GLOBAL_FORM", "1") == "1"
+b = synth.make_batch(n, L, R, seed=1001, global_form=gf)
+for spec in sys.argv[2:] or [""]:
+    ctx = capi.PhmmContext(0)
+    for kv in [s for s in spec.split(",") if s]:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
+    ctx.set_reference(b.ref)
+    ctx.prepare(b.reads, b.read_off, b.ref_start, b.ref_end, b.in_ops, b.in_off, capi.default_params(band=band))
+    ctx.run()
+    ts = []
+    for _ in range(int(os.environ.get("REPS", "2"))):
+        ctx.run()
+        ts.append(ctx.stats()["ms_fwdbwd"])
+    st = ctx.stats()
+    print("%-40s fwdbwd %9.2f ms  decode %7.2f ms  slots %4d  slotMB %7.1f  cells %.3e  -> %.1f Gcell/s  %.0f GB/s(80B/cell)" % (
+        spec or "(default)", min(ts), st["ms_decode"], st["n_slots"], st["slot_bytes"] / 1e6, st["cells"],
+        st["cells"] / min(ts) * 1e-6, 80.0 * st["cells"] / min(ts) * 1e-6), flush=True)
+    ctx.close()
