@@ -264,7 +264,7 @@ template <int NW, bool SW>
 int fb2_occupancy(size_t smem) {
     int n = 0;
     if (cudaFuncSetAttribute(k_fb2<NW, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fb2<NW, SW>, NW * 32, smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fb2<NW, SW>, (NW + 1) * 32, smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
     return n;
 }
 
@@ -275,9 +275,9 @@ int fb2_occupancy(int nw, bool sw, size_t smem) {
 }
 
 void fb2_launch(int nw, bool sw, const Fb2Args &a, int slots, size_t smem, cudaStream_t st) {
-    if (nw == 2) { if (sw) k_fb2<2, true><<<slots, 64, smem, st>>>(a); else k_fb2<2, false><<<slots, 64, smem, st>>>(a); }
-    else if (nw == 4) { if (sw) k_fb2<4, true><<<slots, 128, smem, st>>>(a); else k_fb2<4, false><<<slots, 128, smem, st>>>(a); }
-    else { if (sw) k_fb2<8, true><<<slots, 256, smem, st>>>(a); else k_fb2<8, false><<<slots, 256, smem, st>>>(a); }
+    if (nw == 2) { if (sw) k_fb2<2, true><<<slots, 96, smem, st>>>(a); else k_fb2<2, false><<<slots, 96, smem, st>>>(a); }
+    else if (nw == 4) { if (sw) k_fb2<4, true><<<slots, 160, smem, st>>>(a); else k_fb2<4, false><<<slots, 160, smem, st>>>(a); }
+    else { if (sw) k_fb2<8, true><<<slots, 288, smem, st>>>(a); else k_fb2<8, false><<<slots, 288, smem, st>>>(a); }
 }
 
 int32_t pow2_at_least(int32_t v) { int32_t p = 1; while (p < v) p <<= 1; return p; }
@@ -323,16 +323,18 @@ int plan_memory(phmm_ctx *ctx) {
     for (int64_t i = 0; i < nreg; i++) max_live_doubles = std::max(max_live_doubles, b.geom[i].max_live_doubles);
     // the windowed kernel needs a total-probability schedule that looks one traceback point ahead
     b.fast = !b.expect && !ctx->force_legacy && b.params.min_diags >= 2 * (b.params.tb_diags + 1) + 2 &&
-             max_live_doubles + 7 * (int64_t)b.bw + 16 < 0x7ffffff0;
+             max_live_doubles + (FB2_PRE + 2) * 7 * (int64_t)b.bw + 16 < 0x7ffffff0;
     int occ = 1;
     int64_t slot_bytes = 0;
     if (b.fast) {
         b.nw = ctx->opt_warps ? ctx->opt_warps : (avgw <= 48.0 ? 2 : (avgw <= 112.0 ? 4 : 8));
         b.wg = pow2_at_least(b.bw);
         b.wcap = ctx->opt_wcap ? ctx->opt_wcap : std::max<int32_t>(64, std::min<int32_t>(512, b.wg));
-        b.ring_doubles = max_live_doubles + 7 * (int64_t)b.bw + 16;
+        // the producer warp allocates FB2_PRE diagonals ahead of the compute warps
+        b.ring_doubles = max_live_doubles + (FB2_PRE + 2) * 7 * (int64_t)b.bw + 16;
+        b.dcap += FB2_PRE + 4;
         b.tcap = b.dcap / TOTAL_EVERY + 4;
-        b.fb2_smem = (size_t)2 * NS * b.wcap * 8 + 16 * 8 + sizeof(EmisTables) + 16;
+        b.fb2_smem = (size_t)2 * NS * b.wcap * 8 + (16 + 36) * 8 + 2 * FB2_RQ * sizeof(DiagRec);
         occ = fb2_occupancy(b.nw, sw, b.fb2_smem);
         if (occ < 1) return fail(ctx, PHMM_E_CUDA, "k_fb2 does not fit on this device");
         slot_bytes = b.ring_doubles * 8 + (int64_t)b.dcap * sizeof(DiagRec) + (int64_t)4 * NS * b.wg * 8 +
