@@ -135,14 +135,25 @@ int phmm_realign_batch(phmm_ctx *ctx, int64_t n_reads,
 /* Replaces: `cactus_realign --outputExpectations` over all alignments of one
  * EM iteration (utils.py:528 via cactus_expectationMaximisation).
  * out_stats[0..24] transition expectations from*5+to, [25..104] emission
- * expectations state*16+x*4+y, [105] summed log-likelihood. Values are ADDED
- * to nothing: the array is overwritten with this batch's sums, accumulated in
- * read order so that shards can be combined deterministically. */
+ * expectations state*16+x*4+y, [105] summed log-likelihood.  The array is
+ * overwritten with this batch's sums: the exact integer sums of
+ * phmm_expectations_batch_fixed below, converted to double once. */
 int phmm_expectations_batch(phmm_ctx *ctx, int64_t n_reads,
                             const uint8_t *read_bases, const int64_t *read_off,
                             const int64_t *ref_start, const int64_t *ref_end,
                             const uint32_t *in_cigar_ops, const int64_t *in_cigar_off,
                             const phmm_params *params, double out_stats[106]);
+
+/* Same E-step as exact integers, for deterministic reduction over calls, ranks and GPUs (the reference sums
+ * expectation files in double, utils.py:528 via cactus_expectationMaximisation; integer sums make the trained
+ * HMM independent of how the reads were sharded).  Value k = out_hi[k] + out_lo[k] / 2^32 for k < 105
+ * (0 <= out_lo < 2^32); the log-likelihood k = 105 is out_hi + out_lo / 2^20 with per-region values rounded
+ * to 2^-20.  Add hi to hi and lo to lo (int64) across shards, then convert once. */
+int phmm_expectations_batch_fixed(phmm_ctx *ctx, int64_t n_reads,
+                                  const uint8_t *read_bases, const int64_t *read_off,
+                                  const int64_t *ref_start, const int64_t *ref_end,
+                                  const uint32_t *in_cigar_ops, const int64_t *in_cigar_off,
+                                  const phmm_params *params, int64_t out_hi[106], int64_t out_lo[106]);
 
 /* Split form of phmm_realign_batch for callers that keep a batch resident in
  * HBM (bench.py's kernel-only `value`): prepare = host planning + H2D +

@@ -20,7 +20,7 @@ PHMM_OK = 0
 EXPORTS = [
     "phmm_version", "phmm_default_params", "phmm_create", "phmm_create_error", "phmm_destroy",
     "phmm_last_error", "phmm_set_stream", "phmm_set_model", "phmm_set_reference", "phmm_realign_batch",
-    "phmm_expectations_batch", "phmm_batch_prepare", "phmm_batch_run", "phmm_batch_fetch",
+    "phmm_expectations_batch", "phmm_expectations_batch_fixed", "phmm_batch_prepare", "phmm_batch_run", "phmm_batch_fetch",
     "phmm_batch_get_stats", "phmm_set_memory_budget", "phmm_set_option", "phmm_free", "phmm_free_posteriors",
 ]
 
@@ -82,6 +82,7 @@ def load_library():
     L.phmm_realign_batch.argtypes = batch_in + [C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_int64)),
                                                 C.POINTER(Posteriors)]
     L.phmm_expectations_batch.argtypes = batch_in + [vp]
+    L.phmm_expectations_batch_fixed.argtypes = batch_in + [vp, vp]
     L.phmm_batch_prepare.argtypes = batch_in
     L.phmm_batch_run.argtypes = [vp]
     L.phmm_batch_fetch.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_int64)),
@@ -234,3 +235,12 @@ class PhmmContext:
         out = np.zeros(106, dtype=np.float64)
         self._check(self._lib.phmm_expectations_batch(self._h, n, *[_ptr(x) for x in a], C.byref(params), _ptr(out)))
         return out
+
+    def expectations_batch_fixed(self, reads, read_off, ref_start, ref_end, in_ops, in_off, params):
+        """Returns (hi int64[106], lo int64[106]): exact sums, value = hi + lo / 2^32 (log-likelihood: / 2^20)."""
+        n, a = self._batch_arrays(reads, read_off, ref_start, ref_end, in_ops, in_off)
+        hi = np.zeros(106, dtype=np.int64)
+        lo = np.zeros(106, dtype=np.int64)
+        self._check(self._lib.phmm_expectations_batch_fixed(self._h, n, *[_ptr(x) for x in a], C.byref(params),
+                                                            _ptr(hi), _ptr(lo)))
+        return hi, lo

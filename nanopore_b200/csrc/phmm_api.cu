@@ -870,32 +870,63 @@ int phmm_realign_batch(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases
     return phmm_batch_fetch(ctx, out_cigar_ops, out_cigar_off, post);
 }
 
+// E-step of one batch as exact integers: out_hi[k] + out_lo[k] / 2^32 for the 105 expectations (the kernels
+// accumulate in 2^-32 fixed point), out_hi[105] + out_lo[105] / 2^20 for the summed log-likelihood (per-region
+// values rounded to 2^-20).  Integer sums are independent of the order of regions, reads, calls and ranks.
+static int expectations_fixed(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const int64_t *read_off,
+                              const int64_t *ref_start, const int64_t *ref_end, const uint32_t *in_cigar_ops,
+                              const int64_t *in_cigar_off, const phmm_params *params, int64_t out_hi[106], int64_t out_lo[106]) {
+    int rc = do_prepare(ctx, n_reads, read_bases, read_off, ref_start, ref_end, in_cigar_ops, in_cigar_off, params, true);
+    if (rc) return rc;
+    rc = do_run(ctx);
+    if (rc) return rc;
+    BatchState &b = ctx->b;
+    const int64_t nreg = (int64_t)b.regions.size();
+    std::vector<unsigned long long> T(nreg * 25), E(nreg * 80);
+    std::vector<double> LL(nreg);
+    if (nreg) {
+        CK(cudaMemcpy(T.data(), ctx->d_expT.p, nreg * 25 * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(E.data(), ctx->d_expE.p, nreg * 80 * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(LL.data(), ctx->d_expLL.p, nreg * 8, cudaMemcpyDeviceToHost));
+    }
+    b.stats.d2h_bytes += nreg * (25 + 80 + 1) * 8;
+    __int128 acc[106];
+    for (int k = 0; k < 106; k++) acc[k] = 0;
+    for (int64_t g = 0; g < nreg; g++) {
+        for (int k = 0; k < 25; k++) acc[k] += (__int128)(int64_t)T[g * 25 + k];
+        for (int k = 0; k < 80; k++) acc[25 + k] += (__int128)(int64_t)E[g * 80 + k];
+        acc[105] += (__int128)llrint(LL[g] * 1048576.0);
+    }
+    for (int k = 0; k < 106; k++) {
+        const int bits = k < 105 ? 32 : 20;
+        out_hi[k] = (int64_t)(acc[k] >> bits);                                  // arithmetic shift: floor
+        out_lo[k] = (int64_t)(acc[k] - ((__int128)out_hi[k] << bits));         // in [0, 2^bits)
+    }
+    return PHMM_OK;
+}
+
+int phmm_expectations_batch_fixed(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const int64_t *read_off,
+                                  const int64_t *ref_start, const int64_t *ref_end, const uint32_t *in_cigar_ops,
+                                  const int64_t *in_cigar_off, const phmm_params *params, int64_t out_hi[106],
+                                  int64_t out_lo[106]) {
+    if (!ctx) return PHMM_E_ARG;
+    if (!out_hi || !out_lo) return fail(ctx, PHMM_E_ARG, "out_hi / out_lo is NULL");
+    try {
+        return expectations_fixed(ctx, n_reads, read_bases, read_off, ref_start, ref_end, in_cigar_ops, in_cigar_off, params, out_hi, out_lo);
+    } catch (const std::exception &ex) { return fail(ctx, PHMM_E_NOMEM, ex.what()); }
+}
+
 int phmm_expectations_batch(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const int64_t *read_off,
                             const int64_t *ref_start, const int64_t *ref_end, const uint32_t *in_cigar_ops,
                             const int64_t *in_cigar_off, const phmm_params *params, double out_stats[106]) {
     if (!ctx) return PHMM_E_ARG;
     if (!out_stats) return fail(ctx, PHMM_E_ARG, "out_stats is NULL");
     try {
-        int rc = do_prepare(ctx, n_reads, read_bases, read_off, ref_start, ref_end, in_cigar_ops, in_cigar_off, params, true);
+        int64_t hi[106], lo[106];
+        int rc = expectations_fixed(ctx, n_reads, read_bases, read_off, ref_start, ref_end, in_cigar_ops, in_cigar_off, params, hi, lo);
         if (rc) return rc;
-        rc = do_run(ctx);
-        if (rc) return rc;
-        BatchState &b = ctx->b;
-        const int64_t nreg = (int64_t)b.regions.size();
-        std::vector<unsigned long long> T(nreg * 25), E(nreg * 80);
-        std::vector<double> LL(nreg);
-        if (nreg) {
-            CK(cudaMemcpy(T.data(), ctx->d_expT.p, nreg * 25 * 8, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(E.data(), ctx->d_expE.p, nreg * 80 * 8, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(LL.data(), ctx->d_expLL.p, nreg * 8, cudaMemcpyDeviceToHost));
-        }
-        for (int k = 0; k < 106; k++) out_stats[k] = 0.0;
-        // fixed order: read by read, region by region -> identical sums for any sharding that keeps read order
-        for (int64_t g = 0; g < nreg; g++) {
-            for (int k = 0; k < 25; k++) out_stats[k] += (double)(int64_t)T[g * 25 + k] / 4294967296.0;
-            for (int k = 0; k < 80; k++) out_stats[25 + k] += (double)(int64_t)E[g * 80 + k] / 4294967296.0;
-            out_stats[105] += LL[g];
-        }
+        for (int k = 0; k < 105; k++) out_stats[k] = (double)hi[k] + (double)lo[k] / 4294967296.0;
+        out_stats[105] = (double)hi[105] + (double)lo[105] / 1048576.0;
         return PHMM_OK;
     } catch (const std::exception &ex) { return fail(ctx, PHMM_E_NOMEM, ex.what()); }
 }

@@ -13,48 +13,8 @@ indels.
 """
 import numpy as np
 
-BASES = np.frombuffer(b"ACGTN", dtype=np.uint8)
-_CODE = np.full(256, 4, dtype=np.uint8)
-for _i, _c in enumerate(b"ACGT"):
-    _CODE[_c] = _i
-    _CODE[ord(chr(_c).lower())] = _i
-
-OP_M, OP_I, OP_D = 0, 1, 2
-
-
-def encode(seq):
-    """str/bytes -> uint8 codes A=0 C=1 G=2 T=3 other=4."""
-    if isinstance(seq, str):
-        seq = seq.encode("ascii")
-    return _CODE[np.frombuffer(seq, dtype=np.uint8)]
-
-
-def decode(codes):
-    return BASES[np.asarray(codes, dtype=np.uint8)].tobytes().decode("ascii")
-
-
-def reverse_complement_codes(codes):
-    c = np.asarray(codes, dtype=np.uint8)[::-1].copy()
-    m = c < 4
-    c[m] = 3 - c[m]
-    return c
-
-
-def pack_ops(ops):
-    """[(code, length), ...] -> uint32 (length<<2)|code, merging neighbours of equal code."""
-    out = []
-    for code, ln in ops:
-        if ln <= 0:
-            continue
-        if out and out[-1][0] == code:
-            out[-1][1] += ln
-        else:
-            out.append([code, ln])
-    return np.array([(ln << 2) | code for code, ln in out], dtype=np.uint32)
-
-
-def unpack_ops(packed):
-    return [(int(v) & 3, int(v) >> 2) for v in np.asarray(packed)]
+from .batch import (BASES, OP_M, OP_I, OP_D, Batch, decode, encode, pack_ops,  # noqa: F401
+                    reverse_complement_codes, unpack_ops)
 
 
 def random_reference(length, rng):
@@ -158,44 +118,6 @@ def globalise(local_ops, start, length, ref_len):
     """Chained-global form (utils.py:344-346,366-382): leading/trailing D to span the reference."""
     ops = [(OP_D, start)] + unpack_ops(local_ops) + [(OP_D, ref_len - start - length)]
     return pack_ops(ops)
-
-
-class Batch:
-    """Packed batch in the layout of include/phmm.h."""
-
-    def __init__(self, ref, reads, read_off, ref_start, ref_end, in_ops, in_off, names=None, reverse=None):
-        self.ref = np.ascontiguousarray(ref, dtype=np.uint8)
-        self.reads = np.ascontiguousarray(reads, dtype=np.uint8)
-        self.read_off = np.ascontiguousarray(read_off, dtype=np.int64)
-        self.ref_start = np.ascontiguousarray(ref_start, dtype=np.int64)
-        self.ref_end = np.ascontiguousarray(ref_end, dtype=np.int64)
-        self.in_ops = np.ascontiguousarray(in_ops, dtype=np.uint32)
-        self.in_off = np.ascontiguousarray(in_off, dtype=np.int64)
-        self.names = names
-        self.reverse = reverse
-
-    @property
-    def n(self):
-        return len(self.read_off) - 1
-
-    def read(self, i):
-        return self.reads[self.read_off[i]:self.read_off[i + 1]]
-
-    def ops(self, i):
-        return self.in_ops[self.in_off[i]:self.in_off[i + 1]]
-
-    def subset(self, idx):
-        idx = np.asarray(idx, dtype=np.int64)
-        reads = [self.read(i) for i in idx]
-        ops = [self.ops(i) for i in idx]
-        return Batch(self.ref,
-                     np.concatenate(reads) if reads else np.zeros(0, np.uint8),
-                     np.concatenate(([0], np.cumsum([len(r) for r in reads]))).astype(np.int64),
-                     self.ref_start[idx], self.ref_end[idx],
-                     np.concatenate(ops) if ops else np.zeros(0, np.uint32),
-                     np.concatenate(([0], np.cumsum([len(o) for o in ops]))).astype(np.int64),
-                     [self.names[i] for i in idx] if self.names else None,
-                     self.reverse[idx] if self.reverse is not None else None)
 
 
 def make_batch(n_reads, read_len, ref_len, seed, sub=0.05, ins=0.04, dele=0.06, global_form=True,

@@ -68,6 +68,8 @@ def lib():
         L.po_expectations.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                       C.POINTER(_Params), C.c_void_p, C.c_void_p, C.POINTER(C.c_double),
                                       C.POINTER(_Stats)]
+        L.po_expectations_fixed.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                            C.POINTER(_Params), C.c_void_p, C.c_void_p, C.POINTER(_Stats)]
         L.po_band.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
         L.po_regions.restype = C.c_int64
         L.po_regions.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]
@@ -187,6 +189,18 @@ def expectations(model, X, Y, in_ops, params, T=None, E=None, loglik=0.0):
     lib().po_expectations(model.h, _p(X), len(X), _p(Y), len(Y), _p(ops), len(ops), C.byref(params), _p(T), _p(E),
                           C.byref(ll), C.byref(st))
     return T, E, ll.value, st.cells
+
+
+def expectations_fixed(model, X, Y, in_ops, params, hi=None, lo=None):
+    """E-step of one read as exact integers, ADDED into hi[106], lo[106] (see po_expectations_fixed)."""
+    X, Y = _u8(X), _u8(Y)
+    ops = np.ascontiguousarray(in_ops, dtype=np.uint32)
+    hi = np.zeros(106, dtype=np.int64) if hi is None else hi
+    lo = np.zeros(106, dtype=np.int64) if lo is None else lo
+    st = _Stats()
+    lib().po_expectations_fixed(model.h, _p(X), len(X), _p(Y), len(Y), _p(ops), len(ops), C.byref(params), _p(hi), _p(lo),
+                                C.byref(st))
+    return hi, lo, st.cells
 
 
 def band(ax, ay, lX, lY, expansion):

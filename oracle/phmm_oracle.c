@@ -750,6 +750,36 @@ void po_expectations(const po_model *m, const uint8_t *X, int64_t lX, const uint
     free(reg); free(ax.v); free(ay.v);
 }
 
+/* Same E-step with exact integer accumulation (include/phmm.h phmm_expectations_batch_fixed): value k is
+ * hi[k] + lo[k] / 2^32 for the 105 expectations, hi + lo / 2^20 for the log-likelihood (per-region values
+ * rounded to 2^-20).  ADDS into hi[106], lo[106] and renormalises lo into [0, 2^bits). */
+void po_expectations_fixed(const po_model *m, const uint8_t *X, int64_t lX, const uint8_t *Y, int64_t lY,
+                           const uint32_t *in_ops, int64_t n_in_ops, const po_params *p,
+                           int64_t *hi, int64_t *lo, po_stats *st) {
+    vec64 ax = {0, 0, NULL}, ay = {0, 0, NULL};
+    anchors_from_ops(in_ops, n_in_ops, p->trim, &ax, &ay);
+    region_t *reg; int64_t nr = make_regions(&ax, &ay, lX, lY, p->split_side, &reg);
+    for (int64_t i = 0; i < nr; i++) {
+        int64_t na = reg[i].a1 - reg[i].a0;
+        int64_t *lax = (int64_t *)malloc(sizeof(int64_t) * (size_t)(na + 1)), *lay = (int64_t *)malloc(sizeof(int64_t) * (size_t)(na + 1));
+        for (int64_t k = 0; k < na; k++) { lax[k] = ax.v[reg[i].a0 + k] - reg[i].x1; lay[k] = ay.v[reg[i].a0 + k] - reg[i].y1; }
+        expect_acc acc; memset(&acc, 0, sizeof(acc));
+        double ll = 0.0;
+        posteriors_banded(m, X + reg[i].x1, reg[i].x2 - reg[i].x1, Y + reg[i].y1, reg[i].y2 - reg[i].y1, lax, lay, na, p,
+                          reg[i].rl, reg[i].rr, 1, NULL, 0, 0, &acc, &ll, st);
+        for (int k = 0; k < 106; k++) {
+            const int bits = k < 105 ? 32 : 20;
+            int64_t q = k < 25 ? acc.T[k] : (k < 105 ? acc.E[k - 25] : (int64_t)llrint(ll * 1048576.0));
+            int64_t qh = q >> bits;                       /* arithmetic shift: floor */
+            lo[k] += q - (qh << bits);
+            hi[k] += qh + (lo[k] >> bits);
+            lo[k] &= (((int64_t)1) << bits) - 1;
+        }
+        free(lax); free(lay);
+    }
+    free(reg); free(ax.v); free(ay.v);
+}
+
 /* ---- introspection helpers for tests ---- */
 
 /* band of one region: writes xmyL,xmyR for xay = 0..lX+lY */

@@ -1,0 +1,65 @@
+"""Multi-rank path on CPU: world_size 2 over gloo.  Reads are sharded by cost, realigned per rank and
+re-joined in input order; EM statistics are all-reduced as exact integers, so two ranks give the bits of one."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+
+from nanopore_b200 import capi, parallel, synth
+from nanopore_b200.engine import FixedStats
+from nanopore_b200.hmm import Hmm
+
+from oracle_ctx import oracle_realigner_factory
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_shard_reads_is_balanced_and_deterministic():
+    cost = np.array([100, 5, 80, 80, 7, 60, 1, 300])
+    parts = parallel.shard_reads(cost, 3)
+    assert sorted(np.concatenate(parts).tolist()) == list(range(8))
+    loads = [int(cost[p].sum()) for p in parts]
+    assert max(loads) == 300 and sorted(loads)[0] >= 160                 # LPT: the long read alone, the rest split
+    assert all(np.array_equal(a, b) for a, b in zip(parts, parallel.shard_reads(cost, 3)))
+    assert all((np.diff(p) > 0).all() for p in parts if len(p) > 1)      # input order inside a shard
+    assert [len(p) for p in parallel.shard_reads(np.array([5]), 4)] == [1, 0, 0, 0]
+
+
+def test_world_size_2_matches_single_rank(tmp_path):
+    out = str(tmp_path / "rank0.json")
+    port = free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_dist_worker.py"), out], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        o, _ = p.communicate(timeout=300)
+        assert p.returncode == 0, o
+    got = json.load(open(out))
+    assert all(len(s) > 0 for s in got["shards"])
+    # single-process run of the same work
+    lengths = [150, 420, 90, 300, 260, 510, 33]
+    b = synth.make_batch(len(lengths), 0, 1500, seed=31, lengths=lengths)
+    p = capi.default_params(band=10, split_side=300)
+    r = oracle_realigner_factory()(None)
+    r.set_reference(b.ref)
+    ops, off, _ = r.realign(b, p)
+    assert got["ops"] == ops.tolist() and got["off"] == off.tolist() and got["cells"] == r.cells
+    st = r.expectations(b, p)
+    assert FixedStats(got["hi"], got["lo"]) == st                        # exact: independent of the sharding
+    r.set_hmm(Hmm.loadHmm(os.path.join(HERE, "golden", "blasr_hmm_0.txt")))
+    ops2, off2, _ = r.realign(b, p)
+    assert got["ops_trained"] == ops2.tolist() and got["off_trained"] == off2.tolist()
+    assert got["ops_trained"] != got["ops"]                              # the broadcast model was really used
