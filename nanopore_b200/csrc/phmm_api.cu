@@ -327,7 +327,9 @@ int plan_memory(phmm_ctx *ctx) {
     int occ = 1;
     int64_t slot_bytes = 0;
     if (b.fast) {
-        b.nw = ctx->opt_warps ? ctx->opt_warps : (avgw <= 48.0 ? 2 : (avgw <= 112.0 ? 4 : 8));
+        // measured on B200 (profiles/r01_tune_warps.txt): 4 compute warps x 4 resident regions per SM beat 8 x 2 even at
+        // mean width 158 (fewer warps idle at the per-diagonal barrier); 8 only pays for very wide bands
+        b.nw = ctx->opt_warps ? ctx->opt_warps : (avgw <= 48.0 ? 2 : (avgw <= 320.0 ? 4 : 8));
         b.wg = pow2_at_least(b.bw);
         b.wcap = ctx->opt_wcap ? ctx->opt_wcap : std::max<int32_t>(64, std::min<int32_t>(512, b.wg));
         // the producer warp allocates FB2_PRE diagonals ahead of the compute warps
