@@ -336,11 +336,11 @@ int plan_memory(phmm_ctx *ctx) {
         b.ring_doubles = max_live_doubles + (FB2_PRE + 2) * 7 * (int64_t)b.bw + 16;
         b.dcap += FB2_PRE + 4;
         b.tcap = b.dcap / TOTAL_EVERY + 4;
-        b.fb2_smem = (size_t)2 * NS * b.wcap * 8 + (16 + 36) * 8 + 2 * FB2_RQ * sizeof(DiagRec);
+        b.fb2_smem = (size_t)2 * CS * b.wcap * 8 + FB2_TAB * 8 + 2 * FB2_RQ * sizeof(DiagRec);
         occ = fb2_occupancy(b.nw, sw, b.fb2_smem);
         if (occ < 1) return fail(ctx, PHMM_E_CUDA, "k_fb2 does not fit on this device");
         slot_bytes = b.ring_doubles * 8 + (int64_t)b.dcap * sizeof(DiagRec) + (int64_t)4 * NS * b.wg * 8 +
-                     (int64_t)2 * NS * b.wcap * 8 + (int64_t)b.tcap * 8;
+                     (int64_t)2 * CS * b.wcap * 8 + (int64_t)b.tcap * 8;
     } else {
         b.nw = avgw <= 40.0 ? 1 : (avgw <= 96.0 ? 2 : 4);
         occ = b.nw == 1 ? occupancy_fwdbwd<1>(sw, b.expect) : b.nw == 2 ? occupancy_fwdbwd<2>(sw, b.expect) : occupancy_fwdbwd<4>(sw, b.expect);
@@ -367,7 +367,7 @@ int plan_memory(phmm_ctx *ctx) {
         ctx->d_fring.release(); ctx->d_bring.release(); ctx->d_dots.release();
         CK(ctx->d_ring.ensure((size_t)want * b.ring_doubles * 8));
         CK(ctx->d_wide.ensure((size_t)want * 4 * NS * b.wg * 8));
-        CK(ctx->d_fsave.ensure((size_t)want * 2 * NS * b.wcap * 8));
+        CK(ctx->d_fsave.ensure((size_t)want * 2 * CS * b.wcap * 8));
         CK(ctx->d_totals.ensure((size_t)want * b.tcap * 8));
     } else {
         ctx->d_ring.release(); ctx->d_wide.release();

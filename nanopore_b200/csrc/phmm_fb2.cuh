@@ -36,8 +36,11 @@ namespace phmm {
 
 constexpr int FB2_RQ = 16;          // record FIFO entries (power of two)
 constexpr int FB2_PRE = 6;          // how many diagonals the producer runs ahead (< FB2_RQ - 2)
-constexpr int REC_TOT = 1;          // DiagRec::pad bits
-constexpr int REC_WIDE = 2;
+constexpr int REC_TOT = 1;          // DiagRec::pad bits: the window evaluates the total probability here
+constexpr int REC_WIDE = 2;         //   wider than the shared-memory buffer: lives in the global fallback buffer
+constexpr int REC_FAST3 = 4;        //   diagonals d-2, d-1, d (+-1 column) fit the shared-memory columns without aliasing
+constexpr int CS = 6;               // doubles per shared-memory column: 5 states + 1 pad (16-byte aligned vector loads)
+constexpr int FB2_TAB = 16 + 25 * CS + 5 * CS + 5 * CS;   // logAdd coefficients + the three (emission + transition) tables
 
 struct Fb2Args {
     const uint8_t *ref;
@@ -57,7 +60,7 @@ struct Fb2Args {
     double *ring;   int64_t ring_doubles;
     DiagRec *dtab;  int32_t dcap;
     double *wide;   int32_t wg;  // 4 x wg x 5 doubles: F even/odd, B even/odd for diagonals wider than wcap
-    double *fsave;               // 2 x wcap x 5 doubles: forward state across a traceback window
+    double *fsave;               // 2 x wcap x CS doubles: forward state across a traceback window
     double *totals; int32_t tcap;
     int32_t wcap;                // shared-memory columns (power of two)
     // outputs
@@ -85,85 +88,123 @@ __device__ __forceinline__ double logadd_t(double x, double y, const char *ctab)
     return ((unsigned)dh * 2u < 0x401E0000u * 2u) ? r : mx;      // |d| < 7.5; false for inf / NaN
 }
 
-__device__ __forceinline__ double ldc(const double *col, int s, bool ok) {
-    return ok ? col[s] : PHMM_NEG_INF;
+// Shared-memory tables of (emission + transition) sums, one padded row of CS doubles per symbol (pair); the
+// scalar definition adds `from + (eP + tP)`, so the parenthesised sum can be taken once per model.
+//   tM[cX*5+cY][s] = eM[cX][cY] + tr[s -> M]                              s = M, sX, sY, lX, lY
+//   tX[cX][0..4]   = eX[cX] + tr[M->sX], tr[sX->sX], tr[sY->sX], tr[M->lX], tr[lX->lX]
+//   tY[cY][0..4]   = eY[cY] + tr[M->sY], tr[sY->sY], tr[sX->sY], tr[M->lY], tr[lY->lY]
+struct Tabs {
+    const double *tM, *tX, *tY;
+    const char *ctab;
+};
+
+// One column of 5 state values.  GUARD: scalar loads through an in-band test (any buffer, any stride);
+// otherwise two 16-byte and one 8-byte load from a CS-strided shared-memory column whose out-of-band
+// neighbours are kept at -inf.
+struct ColV { double M, sX, sY, lX, lY; };
+
+template <bool GUARD>
+__device__ __forceinline__ ColV ld_col(const double *p, bool ok) {
+    ColV c;
+    if (GUARD) {
+        c.M = ok ? p[S_M] : PHMM_NEG_INF; c.sX = ok ? p[S_SX] : PHMM_NEG_INF; c.sY = ok ? p[S_SY] : PHMM_NEG_INF;
+        c.lX = ok ? p[S_LX] : PHMM_NEG_INF; c.lY = ok ? p[S_LY] : PHMM_NEG_INF;
+    } else {
+        const double2 a = *reinterpret_cast<const double2 *>(p);
+        const double2 b = *reinterpret_cast<const double2 *>(p + 2);
+        c.M = a.x; c.sX = a.y; c.sY = b.x; c.lX = b.y; c.lY = p[4];
+    }
+    return c;
 }
 
-// Forward cell from its three predecessor columns (5 states each): lower = (x-1,y), upper = (x,y-1) on
-// diagonal d-1, middle = (x-1,y-1) on d-2.  Transition order of SURVEY.md A.4.
-template <bool SWITCH>
-__device__ __forceinline__ void fwd_cell2(const DevModel &m, const EmisTables &t, const char *ctab,
-                                          const double *pl, bool okl, const double *pu, bool oku,
+template <bool VEC>
+__device__ __forceinline__ void st_col(double *p, const double o[NS]) {
+    if (VEC) {
+        *reinterpret_cast<double2 *>(p) = make_double2(o[0], o[1]);
+        *reinterpret_cast<double2 *>(p + 2) = make_double2(o[2], o[3]);
+        p[4] = o[4];
+    } else {
+#pragma unroll
+        for (int s = 0; s < NS; s++) p[s] = o[s];
+    }
+}
+
+// Forward cell from its three predecessor columns: lower = (x-1,y), upper = (x,y-1) on diagonal d-1,
+// middle = (x-1,y-1) on d-2.  Transition order of SURVEY.md A.4.
+template <bool SWITCH, bool GUARD>
+__device__ __forceinline__ void fwd_cell3(const Tabs &t, const double *pl, bool okl, const double *pu, bool oku,
                                           const double *pm, bool okm, int cX, int cY, double out[NS]) {
-    const double eXc = t.eX[cX], eYc = t.eY[cY], eMc = t.eM[cX * 5 + cY];
+    const double *rM = t.tM + (cX * 5 + cY) * CS, *rX = t.tX + cX * CS, *rY = t.tY + cY * CS;
+    const char *ctab = t.ctab;
     {
-        const double Ml = ldc(pl, S_M, okl), sXl = ldc(pl, S_SX, okl), lXl = ldc(pl, S_LX, okl);
-        double a = Ml + (eXc + m.tr[S_M * 5 + S_SX]);
-        a = logadd_t(a, sXl + (eXc + m.tr[S_SX * 5 + S_SX]), ctab);
-        if (SWITCH) { const double sYl = ldc(pl, S_SY, okl); a = logadd_t(a, sYl + (eXc + m.tr[S_SY * 5 + S_SX]), ctab); }
+        const ColV L = ld_col<GUARD>(pl, okl);
+        double a = L.M + rX[0];
+        a = logadd_t(a, L.sX + rX[1], ctab);
+        if (SWITCH) a = logadd_t(a, L.sY + rX[2], ctab);
         out[S_SX] = a;
-        double b = Ml + (eXc + m.tr[S_M * 5 + S_LX]);
-        b = logadd_t(b, lXl + (eXc + m.tr[S_LX * 5 + S_LX]), ctab);
+        double b = L.M + rX[3];
+        b = logadd_t(b, L.lX + rX[4], ctab);
         out[S_LX] = b;
     }
     {
-        double a = ldc(pm, S_M, okm) + (eMc + m.tr[S_M * 5 + S_M]);
-        a = logadd_t(a, ldc(pm, S_SX, okm) + (eMc + m.tr[S_SX * 5 + S_M]), ctab);
-        a = logadd_t(a, ldc(pm, S_SY, okm) + (eMc + m.tr[S_SY * 5 + S_M]), ctab);
-        a = logadd_t(a, ldc(pm, S_LX, okm) + (eMc + m.tr[S_LX * 5 + S_M]), ctab);
-        a = logadd_t(a, ldc(pm, S_LY, okm) + (eMc + m.tr[S_LY * 5 + S_M]), ctab);
+        const ColV C = ld_col<GUARD>(pm, okm);
+        double a = C.M + rM[0];
+        a = logadd_t(a, C.sX + rM[1], ctab);
+        a = logadd_t(a, C.sY + rM[2], ctab);
+        a = logadd_t(a, C.lX + rM[3], ctab);
+        a = logadd_t(a, C.lY + rM[4], ctab);
         out[S_M] = a;
     }
     {
-        const double Mu = ldc(pu, S_M, oku), sYu = ldc(pu, S_SY, oku), lYu = ldc(pu, S_LY, oku);
-        double a = Mu + (eYc + m.tr[S_M * 5 + S_SY]);
-        a = logadd_t(a, sYu + (eYc + m.tr[S_SY * 5 + S_SY]), ctab);
-        if (SWITCH) { const double sXu = ldc(pu, S_SX, oku); a = logadd_t(a, sXu + (eYc + m.tr[S_SX * 5 + S_SY]), ctab); }
+        const ColV U = ld_col<GUARD>(pu, oku);
+        double a = U.M + rY[0];
+        a = logadd_t(a, U.sY + rY[1], ctab);
+        if (SWITCH) a = logadd_t(a, U.sX + rY[2], ctab);
         out[S_SY] = a;
-        double b = Mu + (eYc + m.tr[S_M * 5 + S_LY]);
-        b = logadd_t(b, lYu + (eYc + m.tr[S_LY * 5 + S_LY]), ctab);
+        double b = U.M + rY[3];
+        b = logadd_t(b, U.lY + rY[4], ctab);
         out[S_LY] = b;
     }
 }
 
 // Backward cell from its three successor columns: pu = (x, y+1), pl = (x+1, y) on diagonal d+1,
 // pm = (x+1, y+1) on d+2.  cXn = X[x], cYn = Y[y]: the symbols those steps consume.
-template <bool SWITCH>
-__device__ __forceinline__ void bwd_cell2(const DevModel &m, const EmisTables &t, const char *ctab,
-                                          const double *pl, bool okl, const double *pu, bool oku,
+template <bool SWITCH, bool GUARD>
+__device__ __forceinline__ void bwd_cell3(const Tabs &t, const double *pl, bool okl, const double *pu, bool oku,
                                           const double *pm, bool okm, int cXn, int cYn, double out[NS]) {
-    const double eXn = t.eX[cXn], eYn = t.eY[cYn], eMn = t.eM[cXn * 5 + cYn];
-    const double Bm = ldc(pm, S_M, okm);
-    const double BsY = ldc(pu, S_SY, oku), BlY = ldc(pu, S_LY, oku);
-    const double BsX = ldc(pl, S_SX, okl), BlX = ldc(pl, S_LX, okl);
+    const double *rM = t.tM + (cXn * 5 + cYn) * CS, *rX = t.tX + cXn * CS, *rY = t.tY + cYn * CS;
+    const char *ctab = t.ctab;
+    const double Bm = (!GUARD || okm) ? pm[S_M] : PHMM_NEG_INF;
+    const double BsY = (!GUARD || oku) ? pu[S_SY] : PHMM_NEG_INF, BlY = (!GUARD || oku) ? pu[S_LY] : PHMM_NEG_INF;
+    const double BsX = (!GUARD || okl) ? pl[S_SX] : PHMM_NEG_INF, BlX = (!GUARD || okl) ? pl[S_LX] : PHMM_NEG_INF;
     {
-        double a = Bm + (eMn + m.tr[S_M * 5 + S_M]);
-        a = logadd_t(a, BsY + (eYn + m.tr[S_M * 5 + S_SY]), ctab);
-        a = logadd_t(a, BlY + (eYn + m.tr[S_M * 5 + S_LY]), ctab);
-        a = logadd_t(a, BsX + (eXn + m.tr[S_M * 5 + S_SX]), ctab);
-        a = logadd_t(a, BlX + (eXn + m.tr[S_M * 5 + S_LX]), ctab);
+        double a = Bm + rM[0];
+        a = logadd_t(a, BsY + rY[0], ctab);
+        a = logadd_t(a, BlY + rY[3], ctab);
+        a = logadd_t(a, BsX + rX[0], ctab);
+        a = logadd_t(a, BlX + rX[3], ctab);
         out[S_M] = a;
     }
     {
-        double a = Bm + (eMn + m.tr[S_SX * 5 + S_M]);
-        if (SWITCH) a = logadd_t(a, BsY + (eYn + m.tr[S_SX * 5 + S_SY]), ctab);
-        a = logadd_t(a, BsX + (eXn + m.tr[S_SX * 5 + S_SX]), ctab);
+        double a = Bm + rM[1];
+        if (SWITCH) a = logadd_t(a, BsY + rY[2], ctab);
+        a = logadd_t(a, BsX + rX[1], ctab);
         out[S_SX] = a;
     }
     {
-        double a = Bm + (eMn + m.tr[S_SY * 5 + S_M]);
-        a = logadd_t(a, BsY + (eYn + m.tr[S_SY * 5 + S_SY]), ctab);
-        if (SWITCH) a = logadd_t(a, BsX + (eXn + m.tr[S_SY * 5 + S_SX]), ctab);
+        double a = Bm + rM[2];
+        a = logadd_t(a, BsY + rY[1], ctab);
+        if (SWITCH) a = logadd_t(a, BsX + rX[2], ctab);
         out[S_SY] = a;
     }
     {
-        double a = Bm + (eMn + m.tr[S_LX * 5 + S_M]);
-        a = logadd_t(a, BlX + (eXn + m.tr[S_LX * 5 + S_LX]), ctab);
+        double a = Bm + rM[3];
+        a = logadd_t(a, BlX + rX[4], ctab);
         out[S_LX] = a;
     }
     {
-        double a = Bm + (eMn + m.tr[S_LY * 5 + S_M]);
-        a = logadd_t(a, BlY + (eYn + m.tr[S_LY * 5 + S_LY]), ctab);
+        double a = Bm + rM[4];
+        a = logadd_t(a, BlY + rY[4], ctab);
         out[S_LY] = a;
     }
 }
@@ -177,12 +218,14 @@ __device__ __forceinline__ double fold_seq(int n, const char *ctab, F f) {
 }
 
 // Producer lane state (shared memory, touched by one thread): band walk, ring allocator, schedule of
-// total-probability diagonals (needs the next two traceback points).
+// total-probability diagonals (needs the next two traceback points), column extent of the last two diagonals.
 struct ProdState {
     BandIter it;
     int d;                      // last diagonal generated
     int roff, rsz;              // ring entry of that diagonal
     int tk, P, TF, Pn, TFn;
+    int c1lo, c1hi, c2lo, c2hi; // columns (x - (d >> 1)) of diagonals d and d-1; empty: lo > hi
+    int wf1, wf2;               // their REC_WIDE bits
 };
 
 __device__ __noinline__ void fb2_produce_init(ProdState *ps, const Run *runs, int nrun, int lx, int ly, int expansion,
@@ -198,6 +241,9 @@ __device__ __noinline__ void fb2_produce_init(ProdState *ps, const Run *runs, in
     const int Pn = ntb > 1 ? tb[1] : nd;
     ps->Pn = Pn;
     ps->TFn = Pn - (Pn == nd ? 0 : tbd);
+    ps->c1lo = 0; ps->c1hi = 0;                 // diagonal 0: the single cell (0,0), column 0
+    ps->c2lo = 1; ps->c2hi = 0;                 // no diagonal -1
+    ps->wf1 = 0; ps->wf2 = 0;
 }
 
 // generates the records of the next `count` diagonals (stops at nd)
@@ -205,6 +251,7 @@ __device__ __noinline__ void fb2_produce(ProdState *ps, int count, int nd, const
                                          int64_t ring_doubles, int wcap, DiagRec *srec, DiagRec *dt, int dcap) {
     BandIter it = ps->it;
     int d = ps->d, roff = ps->roff, rsz = ps->rsz, tk = ps->tk, P = ps->P, TF = ps->TF, Pn = ps->Pn, TFn = ps->TFn;
+    int c1lo = ps->c1lo, c1hi = ps->c1hi, c2lo = ps->c2lo, c2hi = ps->c2hi, wf1 = ps->wf1, wf2 = ps->wf2;
     for (int k = 0; k < count && d < nd; k++) {
         d++;
         int xlo, w;
@@ -221,16 +268,31 @@ __device__ __noinline__ void fb2_produce(ProdState *ps, int count, int nd, const
             Pn = tk + 1 < ntb ? tb[tk + 1] : nd;
             TFn = Pn - (Pn == nd ? 0 : tbd);
         }
-        DiagRec rc; rc.off = off; rc.xlo = xlo; rc.w = w; rc.pad = (tot ? REC_TOT : 0) | (w > wcap ? REC_WIDE : 0);
+        const int clo = xlo - (d >> 1), chi = clo + w - 1;
+        const int wf = w > wcap ? REC_WIDE : 0;
+        int lo = min(clo, c1lo), hi = max(chi, c1hi);
+        if (c2lo <= c2hi) { lo = min(lo, c2lo); hi = max(hi, c2hi); }
+        const bool fast3 = !(wf | wf1 | wf2) && (hi - lo + 3 <= wcap);
+        DiagRec rc; rc.off = off; rc.xlo = xlo; rc.w = w; rc.pad = (tot ? REC_TOT : 0) | wf | (fast3 ? REC_FAST3 : 0);
         srec[d & (FB2_RQ - 1)] = rc;
         dt[d % dcap] = rc;
+        c2lo = c1lo; c2hi = c1hi; wf2 = wf1;
+        c1lo = clo; c1hi = chi; wf1 = wf;
     }
     ps->it = it;
     ps->d = d; ps->roff = roff; ps->rsz = rsz; ps->tk = tk; ps->P = P; ps->TF = TF; ps->Pn = Pn; ps->TFn = TFn;
+    ps->c1lo = c1lo; ps->c1hi = c1hi; ps->c2lo = c2lo; ps->c2hi = c2hi; ps->wf1 = wf1; ps->wf2 = wf2;
 }
 
 constexpr int fb2_min_blocks(int nw) { return nw == 8 ? 2 : (nw == 4 ? 4 : 6); }
 
+// Shared-memory diagonal buffers.  Cell (d, x) lives in column (x - (d >> 1)) & (wcap - 1) of the buffer of parity
+// d & 1, so a cell overwrites its own `middle` predecessor (d-2, x-1) and its `lower` / `upper` predecessors sit in
+// the same and the adjacent column of the other buffer.  INVARIANT kept for both buffers: every column that is not
+// in the band of the diagonal the buffer currently holds contains -inf.  With it the recurrences read their
+// neighbours without any in-band test, whatever the band does at its ends, as long as the columns of three
+// consecutive diagonals (plus one either side) do not alias modulo wcap (REC_FAST3, decided by the producer).
+// Other diagonals take the guarded path and then restore the invariant by clearing every out-of-band column.
 template <int NW, bool SWITCH>
 __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const __grid_constant__ Fb2Args a) {
     constexpr int NC = NW * 32;            // compute threads
@@ -239,10 +301,10 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
     const int tid = threadIdx.x;
     const bool producer = tid >= NC;
     const int wcap = a.wcap, cmask = wcap - 1;
-    double *const sbuf = reinterpret_cast<double *>(smem_raw);                  // [2][wcap][5]
-    double *const sct = sbuf + 2 * NS * wcap;                                    // 4 rows x (c3 c2 c1 c0)
-    EmisTables &tab = *reinterpret_cast<EmisTables *>(sct + 16);
-    DiagRec *const srec = reinterpret_cast<DiagRec *>(sct + 16 + 36);            // [FB2_RQ]
+    double *const sbuf = reinterpret_cast<double *>(smem_raw);                  // [2][wcap][CS]
+    double *const sct = sbuf + 2 * CS * wcap;                                    // 4 rows x (c3 c2 c1 c0)
+    double *const stM = sct + 16, *const stX = stM + 25 * CS, *const stY = stX + 5 * CS;
+    DiagRec *const srec = reinterpret_cast<DiagRec *>(sct + FB2_TAB);            // [2][FB2_RQ]
     __shared__ int s_region;
     __shared__ int s_npairs;
     __shared__ ProdState s_prod;
@@ -253,24 +315,45 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
         sct[8] = -0.004605031767994; sct[9] = 0.063427417320019; sct[10] = 0.695956496475118; sct[11] = 0.514272634594009;
         sct[12] = -0.000458661602210; sct[13] = 0.009695946122598; sct[14] = 0.930734667215156; sct[15] = 0.168037164329057;
     }
-    for (int i = tid; i < 25; i += NTA) tab.eM[i] = a.m.eM[i];
-    if (tid < 5) { tab.eX[tid] = a.m.eX[tid]; tab.eY[tid] = a.m.eY[tid]; }
-    const char *const ctab = reinterpret_cast<const char *>(sct);
+    for (int i = tid; i < 25 * CS; i += NTA) {
+        const int r = i / CS, s = i - r * CS;
+        stM[i] = s < NS ? a.m.eM[r] + a.m.tr[s * 5 + S_M] : 0.0;
+    }
+    if (tid < 5 * CS) {
+        const int c = tid / CS, s = tid - c * CS;
+        const int fx[5] = {S_M * 5 + S_SX, S_SX * 5 + S_SX, S_SY * 5 + S_SX, S_M * 5 + S_LX, S_LX * 5 + S_LX};
+        const int fy[5] = {S_M * 5 + S_SY, S_SY * 5 + S_SY, S_SX * 5 + S_SY, S_M * 5 + S_LY, S_LY * 5 + S_LY};
+        stX[tid] = s < NS ? a.m.eX[c] + a.m.tr[fx[s < NS ? s : 0]] : 0.0;
+        stY[tid] = s < NS ? a.m.eY[c] + a.m.tr[fy[s < NS ? s : 0]] : 0.0;
+    }
+    Tabs tabs;
+    tabs.tM = stM; tabs.tX = stX; tabs.tY = stY; tabs.ctab = reinterpret_cast<const char *>(sct);
+    const char *const ctab = tabs.ctab;
 
     const int slot = blockIdx.x;
     double *const ring = a.ring + (int64_t)slot * a.ring_doubles;
     DiagRec *const dt = a.dtab + (int64_t)slot * a.dcap;
     double *const wide = a.wide + (int64_t)slot * 4 * NS * a.wg;
-    double *const fsave = a.fsave + (int64_t)slot * 2 * NS * wcap;
+    double *const fsave = a.fsave + (int64_t)slot * 2 * CS * wcap;
     double *const totals = a.totals + (int64_t)slot * a.tcap;
     const int wgmask = a.wg - 1;
     const int tbd = a.p.tb_diags + 1;
 
     // column of cell x of a diagonal with half-index h, in shared memory or in the wide buffer `wb` (0..3)
     auto col_ptr = [&](bool is_wide, int par, int wb, int x, int h) -> double * {
-        if (!is_wide) return sbuf + ((par * wcap) + ((x - h) & cmask)) * NS;
+        if (!is_wide) return sbuf + ((par * wcap) + ((x - h) & cmask)) * CS;
         return wide + ((int64_t)(wb + par) * a.wg + ((x - h) & wgmask)) * NS;
     };
+    // -inf into the columns [c0, c1] of buffer `par`, cooperatively by `nthr` threads
+    auto clear_cols = [&](int par, int c0, int c1, int lane, int nthr) {
+        for (int c = c0 + lane; c <= c1; c += nthr) {
+            double *q = sbuf + (par * wcap + (c & cmask)) * CS;
+#pragma unroll
+            for (int s = 0; s < NS; s++) q[s] = PHMM_NEG_INF;
+        }
+    };
+    // every column of buffer `par` outside [clo, clo + w) (band columns, unwrapped; w <= wcap)
+    auto clear_outside = [&](int par, int clo, int w, int lane, int nthr) { clear_cols(par, clo + w, clo + wcap - 1, lane, nthr); };
 
     for (;;) {
         __syncthreads();
@@ -291,7 +374,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                 fb2_produce_init(&s_prod, a.runs + reg.run0, reg.nrun, lx, ly, a.p.expansion, tb, ntb, tbd);
                 fb2_produce(&s_prod, FB2_PRE, nd, tb, ntb, tbd, a.ring_doubles, wcap, srec, dt, a.dcap);
             }
-            // diagonal 0: the single cell (0,0), column 0 of the even buffer
+            // both buffers -inf, then diagonal 0: the single cell (0,0), column 0 of the even buffer
+            for (int i = tid; i < 2 * CS * wcap; i += NTA) sbuf[i] = PHMM_NEG_INF;
+            __syncthreads();
             if (tid < NS) {
                 double v;
                 if (reg.ragged_left) v = (tid == S_LX || tid == S_LY) ? 0.0 : PHMM_NEG_INF;
@@ -307,31 +392,36 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
             for (int d = 1; d <= nd; d++) {
                 const DiagRec rc = srec[d & (FB2_RQ - 1)];
                 const int xlo = rc.xlo, w = rc.w;
+                const int h0 = d >> 1, par = d & 1;
+                const int clo = xlo - h0;                             // first column of this diagonal (unwrapped)
+                const bool fast = (rc.pad & REC_FAST3) != 0;
                 if (producer) {
                     if (tid == NC) fb2_produce(&s_prod, 1, nd, tb, ntb, tbd, a.ring_doubles, wcap, srec, dt, a.dcap);   // diagonal d + FB2_PRE
+                    if (fast && w2 > 0) {
+                        // columns of diagonal d-2 that left the band: back to -inf (nobody reads them during d)
+                        const int clo2 = xlo2 - h0 + 1, chi2 = clo2 + w2 - 1, chi = clo + w - 1;
+                        clear_cols(par, clo2, min(clo - 1, chi2), tid - NC, 32);
+                        clear_cols(par, max(chi + 1, clo2), chi2, tid - NC, 32);
+                    }
                 } else {
                     const bool tot = (rc.pad & REC_TOT) != 0;
-                    const int h0 = d >> 1, h1 = (d - 1) >> 1;
                     double *const rg = ring + rc.off;
-                    const int par = d & 1;
-                    if (!((rc.pad | f1 | f2) & REC_WIDE)) {
-                        // fast path: the three diagonals are in shared memory
-                        const double *const b1 = sbuf + (par ^ 1) * wcap * NS;
-                        double *const b0 = sbuf + par * wcap * NS;
-                        for (int i = tid; i < w; i += NC) {
+                    if (fast) {
+                        // the three diagonals are in shared memory and every out-of-band neighbour reads -inf
+                        double *const b0 = sbuf + par * wcap * CS;
+                        const double *const b1 = sbuf + (par ^ 1) * wcap * CS;
+                        const int dl = par ? -1 : 0;                  // lower is in column c-1 (odd d) or c (even d); upper one further
+                        for (int i = (tid - clo) & (NC - 1); i < w; i += NC) {
                             const int x = xlo + i, y = d - x;
                             const int cX = x >= 1 ? X[x - 1] : 4;
                             const int cY = y >= 1 ? Y[y - 1] : 4;
-                            const bool okl = (unsigned)(x - 1 - xlo1) < (unsigned)w1;
-                            const bool oku = (unsigned)(x - xlo1) < (unsigned)w1;
-                            const bool okm = (unsigned)(x - 1 - xlo2) < (unsigned)w2;
-                            double *const p0 = b0 + ((x - h0) & cmask) * NS;              // own column == middle's
-                            const double *const pl = b1 + ((x - 1 - h1) & cmask) * NS;
-                            const double *const pu = b1 + ((x - h1) & cmask) * NS;
+                            const int c = clo + i;
+                            double *const p0 = b0 + (c & cmask) * CS;                      // own column == middle's
+                            const double *const pl = b1 + ((c + dl) & cmask) * CS;
+                            const double *const pu = b1 + ((c + dl + 1) & cmask) * CS;
                             double o[NS];
-                            fwd_cell2<SWITCH>(a.m, tab, ctab, pl, okl, pu, oku, p0, okm, cX, cY, o);
-#pragma unroll
-                            for (int s = 0; s < NS; s++) p0[s] = o[s];
+                            fwd_cell3<SWITCH, false>(tabs, pl, true, pu, true, p0, true, cX, cY, o);
+                            st_col<true>(p0, o);
                             rg[i] = o[S_M];
                             if (tot) {
 #pragma unroll
@@ -340,7 +430,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                         }
                     } else {
                         const bool wd0 = (rc.pad & REC_WIDE) != 0, wd1 = (f1 & REC_WIDE) != 0, wd2 = (f2 & REC_WIDE) != 0;
-                        const int h2 = (d - 2) >> 1;
+                        const int h1 = (d - 1) >> 1, h2 = (d - 2) >> 1;
                         for (int i = tid; i < w; i += NC) {
                             const int x = xlo + i, y = d - x;
                             const int cX = x >= 1 ? X[x - 1] : 4;
@@ -353,9 +443,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                             const double *const pu = col_ptr(wd1, par ^ 1, 0, x, h1);
                             const double *const pm = col_ptr(wd2, par, 0, x - 1, h2);
                             double o[NS];
-                            fwd_cell2<SWITCH>(a.m, tab, ctab, pl, okl, pu, oku, pm, okm, cX, cY, o);
-#pragma unroll
-                            for (int s = 0; s < NS; s++) p0[s] = o[s];
+                            fwd_cell3<SWITCH, true>(tabs, pl, okl, pu, oku, pm, okm, cX, cY, o);
+                            st_col<false>(p0, o);
                             rg[i] = o[S_M];
                             if (tot) {
 #pragma unroll
@@ -364,6 +453,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                         }
                     }
                 }
+                // guarded diagonal held in shared memory: restore the invariant for its buffer (the cleared columns are
+                // outside the band, and the only column of this buffer a cell reads is its own)
+                if (!fast && !(rc.pad & REC_WIDE)) clear_outside(par, clo, w, tid, NTA);
                 __syncthreads();
                 if (d == P) {
                     // ------------------------- traceback window (traced_to, d] -------------------------
@@ -372,7 +464,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                     const double *endv = (at_end && !reg.ragged_right) ? a.m.endp : a.m.rendp;
                     DiagRec *const srb = srec + FB2_RQ;                                  // backward FIFO
                     if (!at_end) {
-                        for (int i = tid; i < 2 * NS * wcap; i += NTA) fsave[i] = sbuf[i];
+                        for (int i = tid; i < 2 * CS * wcap; i += NTA) fsave[i] = sbuf[i];
                     }
                     if (producer) {
                         for (int k = 0; k < FB2_PRE; k++) {
@@ -381,60 +473,85 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                         }
                     }
                     __syncthreads();
+                    // the backward sweep reuses the two buffers: all -inf before its first diagonal
+                    for (int i = tid; i < 2 * CS * wcap; i += NTA) sbuf[i] = PHMM_NEG_INF;
+                    __syncthreads();
                     // phase 1: backward sweep
                     {
                         int bxlo1 = 0, bw1 = 0, bf1 = 0, bxlo2 = 0, bw2 = 0, bf2 = 0;      // diagonals dd+1, dd+2
                         for (int dd = d; dd > traced_to; dd--) {
                             const DiagRec rb = srb[dd & (FB2_RQ - 1)];
+                            const int hb0 = dd >> 1, bpar = dd & 1;
+                            const int bclo = rb.xlo - hb0;
+                            // fast: diagonals dd, dd+1, dd+2 are a FAST3 triple (flag of dd+2) and all exist
+                            const bool bfast = dd + 2 <= d && (bf2 & REC_FAST3) != 0;
                             if (producer) {
                                 const int dn = dd - FB2_PRE;
                                 if (dn > traced_to && tid == NC) srb[dn & (FB2_RQ - 1)] = dt[dn % a.dcap];
+                                if (bfast) {
+                                    const int clo2 = bxlo2 - hb0 - 1, chi2 = clo2 + bw2 - 1, chi = bclo + rb.w - 1;
+                                    clear_cols(bpar, clo2, min(bclo - 1, chi2), tid - NC, 32);
+                                    clear_cols(bpar, max(chi + 1, clo2), chi2, tid - NC, 32);
+                                }
                             } else {
-                                const int h0 = dd >> 1, h1 = (dd + 1) >> 1;
-                                const int par = dd & 1;
                                 double *const rg = ring + rb.off;
                                 const bool dots = (rb.pad & REC_TOT) != 0 && dd <= traced_from;
-                                const bool fastb = !((rb.pad | bf1 | bf2) & REC_WIDE);
-                                const bool wd0 = (rb.pad & REC_WIDE) != 0, wd1 = (bf1 & REC_WIDE) != 0, wd2 = (bf2 & REC_WIDE) != 0;
-                                const int h2 = (dd + 2) >> 1;
-                                for (int i = tid; i < rb.w; i += NC) {
-                                    const int x = rb.xlo + i, y = dd - x;
-                                    double o[NS];
-                                    double *p0;
-                                    if (fastb) p0 = sbuf + (par * wcap + ((x - h0) & cmask)) * NS;
-                                    else p0 = col_ptr(wd0, par, 2, x, h0);
-                                    if (dd < d) {
+                                if (bfast) {
+                                    double *const b0 = sbuf + bpar * wcap * CS;
+                                    const double *const b1 = sbuf + (bpar ^ 1) * wcap * CS;
+                                    const int du = bpar ? -1 : 0;     // (x, y+1) is in column c-1 (odd dd) or c (even dd); (x+1, y) one further
+                                    for (int i = (tid - bclo) & (NC - 1); i < rb.w; i += NC) {
+                                        const int x = rb.xlo + i, y = dd - x;
                                         const int cXn = x < lx ? X[x] : 4;
                                         const int cYn = y < ly ? Y[y] : 4;
-                                        const bool oku = (unsigned)(x - bxlo1) < (unsigned)bw1;
-                                        const bool okl = (unsigned)(x + 1 - bxlo1) < (unsigned)bw1;
-                                        const bool okm = (unsigned)(x + 1 - bxlo2) < (unsigned)bw2;
-                                        if (fastb) {
-                                            const double *const b1 = sbuf + (par ^ 1) * wcap * NS;
-                                            const double *const pu = b1 + ((x - h1) & cmask) * NS;
-                                            const double *const pl = b1 + ((x + 1 - h1) & cmask) * NS;
-                                            bwd_cell2<SWITCH>(a.m, tab, ctab, pl, okl, pu, oku, p0, okm, cXn, cYn, o);
-                                        } else {
-                                            const double *const pu = col_ptr(wd1, par ^ 1, 2, x, h1);
-                                            const double *const pl = col_ptr(wd1, par ^ 1, 2, x + 1, h1);
-                                            const double *const pm = col_ptr(wd2, par, 2, x + 1, h2);
-                                            bwd_cell2<SWITCH>(a.m, tab, ctab, pl, okl, pu, oku, pm, okm, cXn, cYn, o);
+                                        const int c = bclo + i;
+                                        double *const p0 = b0 + (c & cmask) * CS;                  // own column == (x+1, y+1)'s
+                                        const double *const pu = b1 + ((c + du) & cmask) * CS;
+                                        const double *const pl = b1 + ((c + du + 1) & cmask) * CS;
+                                        double o[NS];
+                                        bwd_cell3<SWITCH, false>(tabs, pl, true, pu, true, p0, true, cXn, cYn, o);
+                                        st_col<true>(p0, o);
+                                        rg[rb.w + i] = o[S_M];
+                                        if (dots) {
+                                            double t = rg[i] + o[S_M];
+#pragma unroll
+                                            for (int s = 1; s < NS; s++) t = logadd_t(t, rg[(s + 1) * rb.w + i] + o[s], ctab);
+                                            rg[6 * rb.w + i] = t;
                                         }
-                                    } else {
-#pragma unroll
-                                        for (int s = 0; s < NS; s++) o[s] = endv[s];
                                     }
+                                } else {
+                                    const bool wd0 = (rb.pad & REC_WIDE) != 0, wd1 = (bf1 & REC_WIDE) != 0, wd2 = (bf2 & REC_WIDE) != 0;
+                                    const int h1 = (dd + 1) >> 1, h2 = (dd + 2) >> 1;
+                                    for (int i = tid; i < rb.w; i += NC) {
+                                        const int x = rb.xlo + i, y = dd - x;
+                                        double o[NS];
+                                        double *const p0 = col_ptr(wd0, bpar, 2, x, hb0);
+                                        if (dd < d) {
+                                            const int cXn = x < lx ? X[x] : 4;
+                                            const int cYn = y < ly ? Y[y] : 4;
+                                            const bool oku = (unsigned)(x - bxlo1) < (unsigned)bw1;
+                                            const bool okl = (unsigned)(x + 1 - bxlo1) < (unsigned)bw1;
+                                            const bool okm = (unsigned)(x + 1 - bxlo2) < (unsigned)bw2;
+                                            const double *const pu = col_ptr(wd1, bpar ^ 1, 2, x, h1);
+                                            const double *const pl = col_ptr(wd1, bpar ^ 1, 2, x + 1, h1);
+                                            const double *const pm = col_ptr(wd2, bpar, 2, x + 1, h2);
+                                            bwd_cell3<SWITCH, true>(tabs, pl, okl, pu, oku, pm, okm, cXn, cYn, o);
+                                        } else {
 #pragma unroll
-                                    for (int s = 0; s < NS; s++) p0[s] = o[s];
-                                    rg[rb.w + i] = o[S_M];
-                                    if (dots) {
-                                        double t = rg[i] + o[S_M];
+                                            for (int s = 0; s < NS; s++) o[s] = endv[s];
+                                        }
+                                        st_col<false>(p0, o);
+                                        rg[rb.w + i] = o[S_M];
+                                        if (dots) {
+                                            double t = rg[i] + o[S_M];
 #pragma unroll
-                                        for (int s = 1; s < NS; s++) t = logadd_t(t, rg[(s + 1) * rb.w + i] + o[s], ctab);
-                                        rg[6 * rb.w + i] = t;
+                                            for (int s = 1; s < NS; s++) t = logadd_t(t, rg[(s + 1) * rb.w + i] + o[s], ctab);
+                                            rg[6 * rb.w + i] = t;
+                                        }
                                     }
                                 }
                             }
+                            if (!bfast && !(rb.pad & REC_WIDE)) clear_outside(bpar, bclo, rb.w, tid, NTA);
                             bxlo2 = bxlo1; bw2 = bw1; bf2 = bf1;
                             bxlo1 = rb.xlo; bw1 = rb.w; bf1 = rb.pad;
                             __syncthreads();
@@ -484,7 +601,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                     __syncthreads();
                     // phase 4: forward state back, next window
                     if (!at_end) {
-                        for (int i = tid; i < 2 * NS * wcap; i += NTA) sbuf[i] = fsave[i];
+                        for (int i = tid; i < 2 * CS * wcap; i += NTA) sbuf[i] = fsave[i];
                         __syncthreads();
                     }
                     traced_to = traced_from;
