@@ -13,8 +13,10 @@ only collectives are the start-up broadcast of reference + HMM and the max-reduc
 value      reads/s, inputs and outputs resident in HBM (phmm_batch_run: kernels only)
 e2e        reads/s through the host-buffer entry point phmm_realign_batch (host planning, H2D, kernels,
            D2H, CIGAR assembly all inside the timed region)
-roofline   dominant kernel k_fwdbwd: 80 algorithmic bytes per DP cell (5 fp64 forward values written once
-           and read back once) / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
+roofline   dominant kernel k_fb2 (forward / backward / posterior): 80 algorithmic bytes per DP cell (5 fp64
+           forward values written once and read back once) / its CUDA-event time on
+           the library's stream, against MEASURED_PEAKS.json hbm_gbs; `traffic` is the ncu DRAM traffic per launch
+           scaled from the committed capture (profiles/), bytes per cell x cells of this launch
 cpu_baseline  the CPU oracle (oracle/phmm_oracle.c, a port: the reference's cactus_realign sources are
            absent) on a bounded sample of the same reads, one read per task on all host cores
 
@@ -54,6 +56,19 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
+
+
+TRAFFIC_SRC = "profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one k_fb2 launch / its cells"
+
+
+def traffic_per_cell():
+    """DRAM bytes per DP cell of k_fb2 from the committed `ncu --set full` capture (None if absent)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        t = json.load(open(p))
+        return (float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])) / float(t["cells"])
+    except Exception:
+        return None
 
 
 def peaks():
@@ -282,8 +297,9 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": dict(workload_config(args), l2="working set (forward windows, %.1f GB of scratch) exceeds the 126 MB L2"
                                % (st["slot_bytes"] * st["n_slots"] / 1e9), parallelism="reads sharded by rank, %d per GPU" % args.reads),
-                "roofline": {"bound": "hbm", "kernel": "k_fwdbwd", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "roofline": {"bound": "hbm", "kernel": "k_fb2", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic_per_cell() * cells_rank if traffic_per_cell() else None,
+                             "traffic_source": TRAFFIC_SRC,
                              "algorithmic_bytes_per_launch": BYTES_PER_CELL * cells_rank, "cells_per_launch": cells_rank,
                              "kernel_ms": fb_ms / args.steps, "kernel_share_of_step": fb_ms / ms,
                              "frac_of_datasheet_8TBs": achieved / 8000.0},

@@ -178,6 +178,10 @@ int phmm_set_memory_budget(phmm_ctx *ctx, int64_t bytes);
  *                      windowed shared-memory kernel; results are identical
  *   "warps"         0 = choose by band width, else 2, 4 or 8 warps per DP region
  *   "smem_columns"  0 = choose, else the shared-memory diagonal buffer (power of two, 64..1024)
+ *   "timing_experiment" bit mask that SKIPS parts of the windowed kernel to time the rest (1 forward sequence
+ *                      loads, 2 forward ring stores, 16 traceback windows, 32 forward cells, 64 totals,
+ *                      128 posteriors, 256 backward cells).  Results are WRONG when non-zero; used only by
+ *                      scripts/tune.py for the phase breakdown in profiles/.  0 (default) = the real kernel.
  * Returns PHMM_E_ARG for an unknown name or value. */
 int phmm_set_option(phmm_ctx *ctx, const char *name, int64_t value);
 

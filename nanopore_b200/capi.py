@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphmm_sm100.so")
+LIB_PATH = os.environ.get("PHMM_LIB") or os.path.join(_HERE, "libphmm_sm100.so")      # PHMM_LIB: tuning builds of the same library
 
 PHMM_OK = 0
 EXPORTS = [

@@ -78,7 +78,7 @@ struct phmm_ctx {
     DevModel model;
     int64_t mem_budget = 0;
     bool force_legacy = false;
-    int opt_warps = 0, opt_wcap = 0;             // tests: run the first-generation kernel (k_fwdbwd) instead of k_fb2
+    int opt_warps = 0, opt_wcap = 0, opt_dbg = 0;             // tests: run the first-generation kernel (k_fwdbwd) instead of k_fb2
     DevBuf d_ref; int64_t ref_len = -1;
     DevBuf d_reads, d_regions, d_runs, d_geom, d_order, d_counter;
     DevBuf d_fring, d_dtab, d_bring, d_dots;
@@ -323,7 +323,8 @@ int plan_memory(phmm_ctx *ctx) {
     for (int64_t i = 0; i < nreg; i++) max_live_doubles = std::max(max_live_doubles, b.geom[i].max_live_doubles);
     // the windowed kernel needs a total-probability schedule that looks one traceback point ahead
     b.fast = !b.expect && !ctx->force_legacy && b.params.min_diags >= 2 * (b.params.tb_diags + 1) + 2 &&
-             max_live_doubles + (FB2_PRE + 2) * 7 * (int64_t)b.bw + 16 < 0x7ffffff0;
+             b.params.min_diags - b.params.tb_diags - 1 > FB2_PRE + 2 &&     // the producer never runs two traceback points ahead
+             max_live_doubles + (FB2_PRE + 2) * 6 * (int64_t)b.bw + 16 < 0x7ffffff0;
     int occ = 1;
     int64_t slot_bytes = 0;
     if (b.fast) {
@@ -333,14 +334,14 @@ int plan_memory(phmm_ctx *ctx) {
         b.wg = pow2_at_least(b.bw);
         b.wcap = ctx->opt_wcap ? ctx->opt_wcap : std::max<int32_t>(64, std::min<int32_t>(512, b.wg));
         // the producer warp allocates FB2_PRE diagonals ahead of the compute warps
-        b.ring_doubles = max_live_doubles + (FB2_PRE + 2) * 7 * (int64_t)b.bw + 16;
+        b.ring_doubles = max_live_doubles + (FB2_PRE + 2) * 6 * (int64_t)b.bw + 16;
         b.dcap += FB2_PRE + 4;
         b.tcap = b.dcap / TOTAL_EVERY + 4;
         b.fb2_smem = (size_t)2 * CS * b.wcap * 8 + FB2_TAB * 8 + 2 * FB2_RQ * sizeof(DiagRec);
         occ = fb2_occupancy(b.nw, sw, b.fb2_smem);
         if (occ < 1) return fail(ctx, PHMM_E_CUDA, "k_fb2 does not fit on this device");
         slot_bytes = b.ring_doubles * 8 + (int64_t)b.dcap * sizeof(DiagRec) + (int64_t)4 * NS * b.wg * 8 +
-                     (int64_t)2 * CS * b.wcap * 8 + (int64_t)b.tcap * 8;
+                     (int64_t)2 * CS * b.wcap * 8 + ((int64_t)b.tcap + b.wg) * 8;
     } else {
         b.nw = avgw <= 40.0 ? 1 : (avgw <= 96.0 ? 2 : 4);
         occ = b.nw == 1 ? occupancy_fwdbwd<1>(sw, b.expect) : b.nw == 2 ? occupancy_fwdbwd<2>(sw, b.expect) : occupancy_fwdbwd<4>(sw, b.expect);
@@ -368,7 +369,7 @@ int plan_memory(phmm_ctx *ctx) {
         CK(ctx->d_ring.ensure((size_t)want * b.ring_doubles * 8));
         CK(ctx->d_wide.ensure((size_t)want * 4 * NS * b.wg * 8));
         CK(ctx->d_fsave.ensure((size_t)want * 2 * CS * b.wcap * 8));
-        CK(ctx->d_totals.ensure((size_t)want * b.tcap * 8));
+        CK(ctx->d_totals.ensure((size_t)want * ((size_t)b.tcap + b.wg) * 8));
     } else {
         ctx->d_ring.release(); ctx->d_wide.release();
         CK(ctx->d_fring.ensure((size_t)want * b.ring_cells * NS * 8));
@@ -523,6 +524,7 @@ int do_run(phmm_ctx *ctx) {
         f2.wide = ctx->d_wide.as<double>(); f2.wg = b.wg;
         f2.fsave = ctx->d_fsave.as<double>(); f2.totals = ctx->d_totals.as<double>(); f2.tcap = b.tcap;
         f2.wcap = b.wcap;
+        f2.dbg = ctx->opt_dbg;
         f2.px = fa.px; f2.py = fa.py; f2.pw = fa.pw; f2.npairs = fa.npairs;
         fb2_launch(b.nw, ctx->model.has_switch != 0, f2, b.fb_slots, b.fb2_smem, ctx->stream);
         CK(cudaGetLastError());
@@ -681,6 +683,8 @@ int phmm_set_option(phmm_ctx *ctx, const char *name, int64_t value) {
     else if (n == "warps") {
         if (value != 0 && value != 2 && value != 4 && value != 8) return fail(ctx, PHMM_E_ARG, "warps must be 0, 2, 4 or 8");
         ctx->opt_warps = (int)value;
+    } else if (n == "timing_experiment") {
+        ctx->opt_dbg = (int)value;
     } else if (n == "smem_columns") {
         if (value != 0 && (value < 64 || value > 1024 || (value & (value - 1)))) return fail(ctx, PHMM_E_ARG, "smem_columns must be 0 or a power of two in [64, 1024]");
         ctx->opt_wcap = (int)value;

@@ -38,7 +38,7 @@ struct RegionGeom {                   // written by the geometry kernel
     int32_t max_live_diags;
     int32_t tracebacks;
     int32_t diagonals;
-    int64_t max_live_doubles;         // peak of the windowed kernel's ring (2 or 7 doubles per cell, see phmm_fb2.cuh)
+    int64_t max_live_doubles;         // peak of the windowed kernel's ring (1 or 6 doubles per cell, see phmm_fb2.cuh)
 };
 
 struct DevModel {                     // log-space stateMachine5

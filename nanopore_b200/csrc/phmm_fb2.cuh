@@ -15,10 +15,9 @@
 // one 16-byte record per diagonal instead of re-deriving the geometry 256 times.
 //
 // HBM holds, per live diagonal, only what a later phase needs (the "ring", recycled per traceback window):
-//     F_M  (forward match state)        every diagonal        -> posterior, step-over term of the total
-//     B_M  (backward match state)       every diagonal        -> posterior, step-over term of the total
-//     F_sX F_sY F_lX F_lY + cell dots   every 10th diagonal   -> total probability
-// i.e. 2 doubles per cell, 7 on the diagonals where the window evaluates the total probability.
+//     F_M, overwritten by F_M + B_M on the way back   every diagonal       -> posterior, step-over term of the total
+//     F_sX F_sY F_lX F_lY + cell dots                 every 10th diagonal  -> total probability
+// i.e. 1 double per cell, 6 on the diagonals where the window evaluates the total probability.
 //
 // A traceback window runs in four block-wide phases:
 //   1 backward sweep from the traceback diagonal, storing B_M and the per-cell dot products,
@@ -34,12 +33,17 @@
 
 namespace phmm {
 
-constexpr int FB2_RQ = 16;          // record FIFO entries (power of two)
-constexpr int FB2_PRE = 6;          // how many diagonals the producer runs ahead (< FB2_RQ - 2)
+constexpr int FB2_RQ = 32;          // record FIFO entries (power of two)
+constexpr int FB2_BATCH = 8;        // the producer warp meets the compute warps at a block barrier every FB2_BATCH diagonals
+constexpr int FB2_AHEAD = 16;       // records ready beyond the current diagonal at such a meeting
+constexpr int FB2_PRE = FB2_AHEAD + FB2_BATCH;   // furthest the producer runs ahead (<= FB2_RQ - FB2_BATCH)
 constexpr int REC_TOT = 1;          // DiagRec::pad bits: the window evaluates the total probability here
 constexpr int REC_WIDE = 2;         //   wider than the shared-memory buffer: lives in the global fallback buffer
 constexpr int REC_FAST3 = 4;        //   diagonals d-2, d-1, d (+-1 column) fit the shared-memory columns without aliasing
-constexpr int CS = 6;               // doubles per shared-memory column: 5 states + 1 pad (16-byte aligned vector loads)
+#ifndef PHMM_CS
+#define PHMM_CS 6
+#endif
+constexpr int CS = PHMM_CS;               // doubles per shared-memory column: 5 states + 1 pad (16-byte aligned vector loads)
 constexpr int FB2_TAB = 16 + 25 * CS + 5 * CS + 5 * CS;   // logAdd coefficients + the three (emission + transition) tables
 
 struct Fb2Args {
@@ -61,11 +65,12 @@ struct Fb2Args {
     DiagRec *dtab;  int32_t dcap;
     double *wide;   int32_t wg;  // 4 x wg x 5 doubles: F even/odd, B even/odd for diagonals wider than wcap
     double *fsave;               // 2 x wcap x CS doubles: forward state across a traceback window
-    double *totals; int32_t tcap;
+    double *totals; int32_t tcap; // per slot: tcap totals, then wg sums F_M + B_M of the diagonal just above the posterior range
     int32_t wcap;                // shared-memory columns (power of two)
     // outputs
     int32_t *px, *py, *pw;
     int32_t *npairs;
+    int32_t dbg;                 // timing experiments only (results are wrong when non-zero)
 };
 
 // log(exp(x)+exp(y)), sonLib's piecewise cubic.  Same value, bit for bit, as
@@ -109,17 +114,19 @@ __device__ __forceinline__ ColV ld_col(const double *p, bool ok) {
     if (GUARD) {
         c.M = ok ? p[S_M] : PHMM_NEG_INF; c.sX = ok ? p[S_SX] : PHMM_NEG_INF; c.sY = ok ? p[S_SY] : PHMM_NEG_INF;
         c.lX = ok ? p[S_LX] : PHMM_NEG_INF; c.lY = ok ? p[S_LY] : PHMM_NEG_INF;
-    } else {
+    } else if (CS % 2 == 0) {
         const double2 a = *reinterpret_cast<const double2 *>(p);
         const double2 b = *reinterpret_cast<const double2 *>(p + 2);
         c.M = a.x; c.sX = a.y; c.sY = b.x; c.lX = b.y; c.lY = p[4];
+    } else {
+        c.M = p[0]; c.sX = p[1]; c.sY = p[2]; c.lX = p[3]; c.lY = p[4];
     }
     return c;
 }
 
 template <bool VEC>
 __device__ __forceinline__ void st_col(double *p, const double o[NS]) {
-    if (VEC) {
+    if (VEC && CS % 2 == 0) {
         *reinterpret_cast<double2 *>(p) = make_double2(o[0], o[1]);
         *reinterpret_cast<double2 *>(p + 2) = make_double2(o[2], o[3]);
         p[4] = o[4];
@@ -209,6 +216,9 @@ __device__ __forceinline__ void bwd_cell3(const Tabs &t, const double *pl, bool 
     }
 }
 
+// barrier of the compute warps only (the producer warp runs ahead between block barriers)
+__device__ __forceinline__ void bar_compute(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
 // left-to-right logAdd fold of n values produced by f(i), starting from -inf (dpDiagonal_dotProduct order)
 template <typename F>
 __device__ __forceinline__ double fold_seq(int n, const char *ctab, F f) {
@@ -258,7 +268,7 @@ __device__ __noinline__ void fb2_produce(ProdState *ps, int count, int nd, const
         it.diag(d, xlo, w);
         const int tf = d <= TF ? TF : TFn;
         const bool tot = (tf - d) % TOTAL_EVERY == 0;
-        const int es = w * (tot ? 7 : 2);
+        const int es = w * (tot ? 6 : 1);
         int off = roff + rsz;
         if ((int64_t)off + es > ring_doubles) off = 0;
         roff = off; rsz = es;
@@ -284,7 +294,10 @@ __device__ __noinline__ void fb2_produce(ProdState *ps, int count, int nd, const
     ps->c1lo = c1lo; ps->c1hi = c1hi; ps->c2lo = c2lo; ps->c2hi = c2hi; ps->wf1 = wf1; ps->wf2 = wf2;
 }
 
-constexpr int fb2_min_blocks(int nw) { return nw == 8 ? 2 : (nw == 4 ? 4 : 6); }
+#ifndef PHMM_MB4
+#define PHMM_MB4 4
+#endif
+constexpr int fb2_min_blocks(int nw) { return nw == 8 ? 2 : (nw == 4 ? PHMM_MB4 : 6); }
 
 // Shared-memory diagonal buffers.  Cell (d, x) lives in column (x - (d >> 1)) & (wcap - 1) of the buffer of parity
 // d & 1, so a cell overwrites its own `middle` predecessor (d-2, x-1) and its `lower` / `upper` predecessors sit in
@@ -335,7 +348,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
     DiagRec *const dt = a.dtab + (int64_t)slot * a.dcap;
     double *const wide = a.wide + (int64_t)slot * 4 * NS * a.wg;
     double *const fsave = a.fsave + (int64_t)slot * 2 * CS * wcap;
-    double *const totals = a.totals + (int64_t)slot * a.tcap;
+    double *const totals = a.totals + (int64_t)slot * (a.tcap + a.wg);
+    double *const ovs = totals + a.tcap;
     const int wgmask = a.wg - 1;
     const int tbd = a.p.tb_diags + 1;
 
@@ -372,7 +386,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
             const int ntb = a.ntb[(int64_t)ridx * a.ntb_stride];
             if (tid == NC) {
                 fb2_produce_init(&s_prod, a.runs + reg.run0, reg.nrun, lx, ly, a.p.expansion, tb, ntb, tbd);
-                fb2_produce(&s_prod, FB2_PRE, nd, tb, ntb, tbd, a.ring_doubles, wcap, srec, dt, a.dcap);
+                fb2_produce(&s_prod, FB2_AHEAD, nd, tb, ntb, tbd, a.ring_doubles, wcap, srec, dt, a.dcap);
             }
             // both buffers -inf, then diagonal 0: the single cell (0,0), column 0 of the even buffer
             for (int i = tid; i < 2 * CS * wcap; i += NTA) sbuf[i] = PHMM_NEG_INF;
@@ -390,31 +404,30 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
             int P = tb[0];
             __syncthreads();
             for (int d = 1; d <= nd; d++) {
+                if (((d - 1) & (FB2_BATCH - 1)) == 0) {
+                    // records up to d + FB2_AHEAD - 1 are published; the producer goes on with the next FB2_BATCH
+                    __syncthreads();
+                    if (tid == NC) fb2_produce(&s_prod, FB2_BATCH, nd, tb, ntb, tbd, a.ring_doubles, wcap, srec, dt, a.dcap);
+                }
                 const DiagRec rc = srec[d & (FB2_RQ - 1)];
                 const int xlo = rc.xlo, w = rc.w;
                 const int h0 = d >> 1, par = d & 1;
                 const int clo = xlo - h0;                             // first column of this diagonal (unwrapped)
                 const bool fast = (rc.pad & REC_FAST3) != 0;
-                if (producer) {
-                    if (tid == NC) fb2_produce(&s_prod, 1, nd, tb, ntb, tbd, a.ring_doubles, wcap, srec, dt, a.dcap);   // diagonal d + FB2_PRE
-                    if (fast && w2 > 0) {
-                        // columns of diagonal d-2 that left the band: back to -inf (nobody reads them during d)
-                        const int clo2 = xlo2 - h0 + 1, chi2 = clo2 + w2 - 1, chi = clo + w - 1;
-                        clear_cols(par, clo2, min(clo - 1, chi2), tid - NC, 32);
-                        clear_cols(par, max(chi + 1, clo2), chi2, tid - NC, 32);
-                    }
-                } else {
+                if (!producer) {
                     const bool tot = (rc.pad & REC_TOT) != 0;
                     double *const rg = ring + rc.off;
-                    if (fast) {
+                    if (a.dbg & 32) {
+                    } else if (fast) {
                         // the three diagonals are in shared memory and every out-of-band neighbour reads -inf
                         double *const b0 = sbuf + par * wcap * CS;
                         const double *const b1 = sbuf + (par ^ 1) * wcap * CS;
                         const int dl = par ? -1 : 0;                  // lower is in column c-1 (odd d) or c (even d); upper one further
                         for (int i = (tid - clo) & (NC - 1); i < w; i += NC) {
                             const int x = xlo + i, y = d - x;
-                            const int cX = x >= 1 ? X[x - 1] : 4;
-                            const int cY = y >= 1 ? Y[y - 1] : 4;
+                            int cX, cY;
+                            if (a.dbg & 1) { cX = x & 3; cY = y & 3; }
+                            else { cX = x >= 1 ? X[x - 1] : 4; cY = y >= 1 ? Y[y - 1] : 4; }
                             const int c = clo + i;
                             double *const p0 = b0 + (c & cmask) * CS;                      // own column == middle's
                             const double *const pl = b1 + ((c + dl) & cmask) * CS;
@@ -422,10 +435,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                             double o[NS];
                             fwd_cell3<SWITCH, false>(tabs, pl, true, pu, true, p0, true, cX, cY, o);
                             st_col<true>(p0, o);
+                            if (!(a.dbg & 2)) {
                             rg[i] = o[S_M];
                             if (tot) {
 #pragma unroll
-                                for (int s = 1; s < NS; s++) rg[(s + 1) * w + i] = o[s];
+                                for (int s = 1; s < NS; s++) rg[s * w + i] = o[s];
+                            }
                             }
                         }
                     } else {
@@ -448,16 +463,32 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                             rg[i] = o[S_M];
                             if (tot) {
 #pragma unroll
-                                for (int s = 1; s < NS; s++) rg[(s + 1) * w + i] = o[s];
+                                for (int s = 1; s < NS; s++) rg[s * w + i] = o[s];
                             }
                         }
                     }
                 }
-                // guarded diagonal held in shared memory: restore the invariant for its buffer (the cleared columns are
-                // outside the band, and the only column of this buffer a cell reads is its own)
-                if (!fast && !(rc.pad & REC_WIDE)) clear_outside(par, clo, w, tid, NTA);
-                __syncthreads();
-                if (d == P) {
+                if (!producer) {
+                    if (fast) {
+                        // columns of diagonal d-2 that left the band: back to -inf (nobody reads them during d)
+                        if (w2 > 0) {
+                            const int clo2 = xlo2 - h0 + 1, chi2 = clo2 + w2 - 1, chi = clo + w - 1;
+                            clear_cols(par, clo2, min(clo - 1, chi2), tid, NC);
+                            clear_cols(par, max(chi + 1, clo2), chi2, tid, NC);
+                        }
+                    } else if (!(rc.pad & REC_WIDE)) {
+                        // guarded diagonal held in shared memory: restore the invariant for its buffer (the cleared columns
+                        // are outside the band, and the only column of this buffer a cell reads is its own)
+                        clear_outside(par, clo, w, tid, NC);
+                    }
+                    bar_compute(NC);
+                }
+                if (d == P && (a.dbg & 16)) {
+                    traced_to = d - (d == nd ? 0 : tbd);
+                    tk++;
+                    P = tk < ntb ? tb[tk] : nd + 1;
+                } else if (d == P) {
+                    __syncthreads();            // the producer warp joins for the traceback window
                     // ------------------------- traceback window (traced_to, d] -------------------------
                     const bool at_end = d == nd;
                     const int traced_from = d - (at_end ? 0 : tbd);
@@ -466,11 +497,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                     if (!at_end) {
                         for (int i = tid; i < 2 * CS * wcap; i += NTA) fsave[i] = sbuf[i];
                     }
-                    if (producer) {
-                        for (int k = 0; k < FB2_PRE; k++) {
-                            const int dd = d - k;
-                            if (dd > traced_to && tid == NC) srb[dd & (FB2_RQ - 1)] = dt[dd % a.dcap];
-                        }
+                    if (producer && tid - NC < FB2_AHEAD) {
+                        const int dd = d - (tid - NC);
+                        if (dd > traced_to) srb[dd & (FB2_RQ - 1)] = dt[dd % a.dcap];
                     }
                     __syncthreads();
                     // the backward sweep reuses the two buffers: all -inf before its first diagonal
@@ -480,23 +509,23 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                     {
                         int bxlo1 = 0, bw1 = 0, bf1 = 0, bxlo2 = 0, bw2 = 0, bf2 = 0;      // diagonals dd+1, dd+2
                         for (int dd = d; dd > traced_to; dd--) {
+                            if (((d - dd) & (FB2_BATCH - 1)) == 0) {
+                                if (dd != d) __syncthreads();
+                                if (producer && tid - NC < FB2_BATCH) {           // records dd-16 .. dd-23 for the batch after next
+                                    const int dn = dd - FB2_AHEAD - (tid - NC);
+                                    if (dn > traced_to) srb[dn & (FB2_RQ - 1)] = dt[dn % a.dcap];
+                                }
+                            }
                             const DiagRec rb = srb[dd & (FB2_RQ - 1)];
                             const int hb0 = dd >> 1, bpar = dd & 1;
                             const int bclo = rb.xlo - hb0;
                             // fast: diagonals dd, dd+1, dd+2 are a FAST3 triple (flag of dd+2) and all exist
                             const bool bfast = dd + 2 <= d && (bf2 & REC_FAST3) != 0;
-                            if (producer) {
-                                const int dn = dd - FB2_PRE;
-                                if (dn > traced_to && tid == NC) srb[dn & (FB2_RQ - 1)] = dt[dn % a.dcap];
-                                if (bfast) {
-                                    const int clo2 = bxlo2 - hb0 - 1, chi2 = clo2 + bw2 - 1, chi = bclo + rb.w - 1;
-                                    clear_cols(bpar, clo2, min(bclo - 1, chi2), tid - NC, 32);
-                                    clear_cols(bpar, max(chi + 1, clo2), chi2, tid - NC, 32);
-                                }
-                            } else {
+                            if (!producer) {
                                 double *const rg = ring + rb.off;
                                 const bool dots = (rb.pad & REC_TOT) != 0 && dd <= traced_from;
-                                if (bfast) {
+                                if (a.dbg & 256) {
+                                } else if (bfast) {
                                     double *const b0 = sbuf + bpar * wcap * CS;
                                     const double *const b1 = sbuf + (bpar ^ 1) * wcap * CS;
                                     const int du = bpar ? -1 : 0;     // (x, y+1) is in column c-1 (odd dd) or c (even dd); (x+1, y) one further
@@ -505,18 +534,23 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                                         const int cXn = x < lx ? X[x] : 4;
                                         const int cYn = y < ly ? Y[y] : 4;
                                         const int c = bclo + i;
+                                        const double fM = rg[i];                                   // issued early, used last
                                         double *const p0 = b0 + (c & cmask) * CS;                  // own column == (x+1, y+1)'s
                                         const double *const pu = b1 + ((c + du) & cmask) * CS;
                                         const double *const pl = b1 + ((c + du + 1) & cmask) * CS;
                                         double o[NS];
                                         bwd_cell3<SWITCH, false>(tabs, pl, true, pu, true, p0, true, cXn, cYn, o);
                                         st_col<true>(p0, o);
-                                        rg[rb.w + i] = o[S_M];
+                                        const double sM = fM + o[S_M];
+                                        // F_M is not needed again below traced_from; above it the next window sweeps the
+                                        // diagonal once more, and only the one next to the range feeds a total
+                                        if (dd <= traced_from) rg[i] = sM;
+                                        else if (dd == traced_from + 1) ovs[i] = sM;
                                         if (dots) {
-                                            double t = rg[i] + o[S_M];
+                                            double t = sM;
 #pragma unroll
-                                            for (int s = 1; s < NS; s++) t = logadd_t(t, rg[(s + 1) * rb.w + i] + o[s], ctab);
-                                            rg[6 * rb.w + i] = t;
+                                            for (int s = 1; s < NS; s++) t = logadd_t(t, rg[s * rb.w + i] + o[s], ctab);
+                                            rg[5 * rb.w + i] = t;
                                         }
                                     }
                                 } else {
@@ -541,47 +575,64 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                                             for (int s = 0; s < NS; s++) o[s] = endv[s];
                                         }
                                         st_col<false>(p0, o);
-                                        rg[rb.w + i] = o[S_M];
+                                        const double sM = rg[i] + o[S_M];
+                                        if (dd <= traced_from) rg[i] = sM;
+                                        else if (dd == traced_from + 1) ovs[i] = sM;
                                         if (dots) {
-                                            double t = rg[i] + o[S_M];
+                                            double t = sM;
 #pragma unroll
-                                            for (int s = 1; s < NS; s++) t = logadd_t(t, rg[(s + 1) * rb.w + i] + o[s], ctab);
-                                            rg[6 * rb.w + i] = t;
+                                            for (int s = 1; s < NS; s++) t = logadd_t(t, rg[s * rb.w + i] + o[s], ctab);
+                                            rg[5 * rb.w + i] = t;
                                         }
                                     }
                                 }
                             }
-                            if (!bfast && !(rb.pad & REC_WIDE)) clear_outside(bpar, bclo, rb.w, tid, NTA);
+                            if (!producer) {
+                                if (bfast) {
+                                    const int clo2 = bxlo2 - hb0 - 1, chi2 = clo2 + bw2 - 1, chi = bclo + rb.w - 1;
+                                    clear_cols(bpar, clo2, min(bclo - 1, chi2), tid, NC);
+                                    clear_cols(bpar, max(chi + 1, clo2), chi2, tid, NC);
+                                } else if (!(rb.pad & REC_WIDE)) {
+                                    clear_outside(bpar, bclo, rb.w, tid, NC);
+                                }
+                                bar_compute(NC);
+                            }
                             bxlo2 = bxlo1; bw2 = bw1; bf2 = bf1;
                             bxlo1 = rb.xlo; bw1 = rb.w; bf1 = rb.pad;
-                            __syncthreads();
                         }
                     }
+                    __syncthreads();
                     // phase 2: total probabilities, one thread per total diagonal
                     const int nk = traced_from > traced_to ? (traced_from - traced_to - 1) / TOTAL_EVERY + 1 : 0;
-                    for (int k = tid; k < nk; k += NTA) {
+                    for (int k = tid; k < ((a.dbg & 64) ? 0 : nk); k += NTA) {
                         const int dd = traced_from - TOTAL_EVERY * k;
                         const DiagRec r0 = dt[dd % a.dcap];
-                        const double *cd = ring + r0.off + 6 * r0.w;
+                        const double *cd = ring + r0.off + 5 * r0.w;
                         double total = fold_seq(r0.w, ctab, [&](int i) { return cd[i]; });
                         if (dd < d) {
                             const DiagRec r1 = dt[(dd + 1) % a.dcap];
-                            const double *fm = ring + r1.off, *bm = fm + r1.w;
-                            const double t1 = fold_seq(r1.w, ctab, [&](int i) { return fm[i] + bm[i]; });
+                            const double *sm = dd + 1 > traced_from ? ovs : ring + r1.off;
+                            const double t1 = fold_seq(r1.w, ctab, [&](int i) { return sm[i]; });
                             total = logadd_t(total, t1, ctab);
                         }
                         totals[k] = total;
                     }
                     __syncthreads();
                     // phase 3: posterior match probabilities, one warp per diagonal
-                    for (int dd = traced_from - (tid >> 5); dd > traced_to; dd -= NW + 1) {
+                    for (int dd = traced_from - (tid >> 5); dd > ((a.dbg & 128) ? traced_from : traced_to); dd -= NW + 1) {
                         const DiagRec r0 = dt[dd % a.dcap];
                         const double total = totals[(traced_from - dd) / TOTAL_EVERY];
-                        const double *fm = ring + r0.off, *bm = fm + r0.w;
-                        for (int i = tid & 31; i < r0.w; i += 32) {
+                        const double *sm = ring + r0.off;
+                        for (int i0 = tid & 31; i0 < r0.w; i0 += 128) {
+                            double sv[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) sv[u] = i0 + 32 * u < r0.w ? sm[i0 + 32 * u] : PHMM_NEG_INF;   // 4 loads in flight
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                            const int i = i0 + 32 * u;
                             const int x = r0.xlo + i, y = dd - x;
-                            if (x > 0 && y > 0) {
-                                const double lp = (fm[i] + bm[i]) - total;
+                            if (i < r0.w && x > 0 && y > 0) {
+                                const double lp = sv[u] - total;
                                 if (lp >= a.p.lp_skip) {
                                     double pr = exp_det(lp);
                                     if (pr >= a.p.threshold) {
@@ -595,6 +646,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                                         }
                                     }
                                 }
+                            }
                             }
                         }
                     }

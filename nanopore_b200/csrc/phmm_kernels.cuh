@@ -90,7 +90,7 @@ __global__ void k_geometry(const Region *regions, const Run *runs, int n_regions
     }
     g.max_live_cells = max_live;
     g.max_live_diags = max_live_d;
-    // second sweep: ring usage of the windowed kernel (2 doubles per cell, 7 on total-probability diagonals)
+    // second sweep: ring usage of the windowed kernel (1 double per cell, 6 on total-probability diagonals)
     g.max_live_doubles = 0;
     if (nd > 0 && g.tracebacks <= tb_cap) {
         it.init(runs + reg.run0, reg.nrun, reg.lx, reg.ly, p.expansion);
@@ -105,7 +105,7 @@ __global__ void k_geometry(const Region *regions, const Run *runs, int n_regions
             it.diag(d, xlo, w);
             const int tf = d <= TF ? TF : TFn;
             const bool tot = (tf - d) % TOTAL_EVERY == 0;
-            const int es = w * (tot ? 7 : 2);
+            const int es = w * (tot ? 6 : 1);
             wbuf[d & 255] = es;
             lv += es;
             if (lv > mx) mx = lv;
