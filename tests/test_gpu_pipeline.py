@@ -1,0 +1,120 @@
+"""The plugin path on the real library (`-m gpu`): SAM in -> chain -> batched realignment on the B200 -> SAM out, EM
+through the E-step kernel, posterior epilogues; every result compared with the same host code driven by the CPU
+checker (bit-exact CIGARs, identical trained HMM files)."""
+import filecmp
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import oracle
+from nanopore_b200 import capi, em, posteriors, realign, synth
+from nanopore_b200.engine import FixedStats, Realigner
+from nanopore_b200.mappers.abstractMapper import AbstractMapper
+from nanopore_b200.target import Stack, Target
+
+from helpers_sam import make_experiment
+from oracle_ctx import oracle_realigner_factory
+
+pytestmark = pytest.mark.gpu
+
+
+class MapperRealign(AbstractMapper):
+    kw = {}
+
+    def run(self):
+        self.realignSamFile(**self.kw)
+
+
+def run_both(tmp_path, cls, seed, **exp):
+    """Runs the mapper plugin twice on copies of one experiment: GPU library, then CPU checker."""
+    outs = []
+    for tag, factory in (("gpu", None), ("cpu", oracle_realigner_factory())):
+        d = str(tmp_path / tag)
+        ref_fa, fq, sam_path, _ = make_experiment(d, seed=seed, **exp)
+        prev = realign.setRealignerFactory(factory) if factory else None
+        try:
+            m = cls(fq, "2D", ref_fa, sam_path, emptyHmmFile=os.path.join(d, "hmm.txt"))
+            assert Stack(m).startJobTree(None) == 0
+        finally:
+            if factory:
+                realign.setRealignerFactory(prev)
+        outs.append(d)
+    return outs
+
+
+def test_realign_sam_file_on_gpu_equals_checker(tmp_path):
+    g, c = run_both(tmp_path, MapperRealign, seed=3, n_reads=12, read_len=700, contig_lens=(4000, 2500))
+    assert filecmp.cmp(os.path.join(g, "mapping.sam"), os.path.join(c, "mapping.sam"), shallow=False)
+
+    class Trained(MapperRealign):
+        kw = dict(useTrainedModel=True, trainedModelFile="blasr_hmm_40.txt", gapGamma=0.3)
+    g, c = run_both(tmp_path / "t", Trained, seed=4, n_reads=8, read_len=500)
+    assert filecmp.cmp(os.path.join(g, "mapping.sam"), os.path.join(c, "mapping.sam"), shallow=False)
+
+
+def test_em_on_gpu_trains_the_same_model_as_the_checker(tmp_path, monkeypatch):
+    fast = em.Options()
+    fast.modelType, fast.randomStart, fast.trials, fast.iterations, fast.trainEmissions = "fiveStateAsymmetric", True, 2, 3, True
+    fast.outputTrialHmms = True
+    orig = em.learnModelFromSamFileTargetFn
+    monkeypatch.setattr(em, "learnModelFromSamFileTargetFn", lambda t, *a: orig(t, *a, options=fast))
+
+    class Em(MapperRealign):
+        kw = dict(doEm=True)
+    g, c = run_both(tmp_path, Em, seed=5, n_reads=10, read_len=400)
+    for f in ("hmm.txt_unnormalised", "hmm.txt", "hmm.txt.xml", "hmm.txt_unnormalised_0", "hmm.txt_unnormalised_1", "mapping.sam"):
+        assert filecmp.cmp(os.path.join(g, f), os.path.join(c, f), shallow=False), f
+
+
+def test_expectations_fixed_point_and_chunking_on_gpu():
+    b = synth.make_batch(9, 600, 2000, seed=13)
+    p = capi.default_params(band=10, split_side=300)
+    r = Realigner(0)
+    r.set_reference(b.ref)
+    st = r.expectations(b, p)
+    hi, lo = np.zeros(106, np.int64), np.zeros(106, np.int64)
+    model, op = oracle.Model(), oracle.make_params(expansion=10, split_side=300)
+    for i in range(b.n):
+        hi, lo, _ = oracle.expectations_fixed(model, b.ref[b.ref_start[i]:b.ref_end[i]], b.read(i), b.ops(i), op, hi, lo)
+    assert st == FixedStats(hi, lo)                                      # exact integers, log-likelihood included
+    small = Realigner(0, max_bases_per_call=6000)
+    small.set_reference(b.ref)
+    assert small.expectations(b, p) == st                                # any chunking gives the same integers
+    o1, f1, p1 = r.realign(b, p, want_posteriors=True)
+    o2, f2, p2 = small.realign(b, p, want_posteriors=True)
+    assert np.array_equal(o1, o2) and np.array_equal(f1, f2) and all(np.array_equal(p1[k], p2[k]) for k in p1)
+    r.close(); small.close()
+
+
+@pytest.mark.parametrize("band,lengths", [
+    (100, [5000] * 3),                                                   # config 3 shape: 5 kb reads, band 100
+    (50, synth.pareto_lengths(10, seed=4, lo=500, hi=20000).tolist()),   # config 5 shape: Pareto mixed lengths
+])
+def test_other_baseline_configs_at_small_scale(band, lengths):
+    b = synth.make_batch(len(lengths), 0, 30000, seed=band, lengths=lengths, sub=0.10, ins=0.06, dele=0.09)
+    ctx = capi.PhmmContext(0)
+    ctx.set_reference(b.ref)
+    ops, off, _ = ctx.realign_batch(b.reads, b.read_off, b.ref_start, b.ref_end, b.in_ops, b.in_off, capi.default_params(band=band))
+    model, op = oracle.Model(), oracle.make_params(expansion=band)
+    for i in range(b.n):
+        r = oracle.realign(model, b.ref[b.ref_start[i]:b.ref_end[i]], b.read(i), b.ops(i), op)
+        assert np.array_equal(r["ops"], ops[off[i]:off[i + 1]]), i
+    ctx.close()
+
+
+def test_alignment_uncertainty_on_gpu_equals_checker(tmp_path):
+    outs = []
+    for tag, factory in (("gpu", None), ("cpu", oracle_realigner_factory())):
+        ref_fa, fq, sam_path, _ = make_experiment(str(tmp_path / tag), n_reads=6, seed=8, hits=(1,))
+        outdir = str(tmp_path / tag / "analysis")
+        os.makedirs(outdir)
+        prev = realign.setRealignerFactory(factory) if factory else None
+        try:
+            assert Stack(posteriors.AlignmentUncertainty(fq, "2D", ref_fa, sam_path, outdir)).startJobTree(None) == 0
+        finally:
+            if factory:
+                realign.setRealignerFactory(prev)
+        outs.append(os.path.join(outdir, "alignmentUncertainty.xml"))
+    assert filecmp.cmp(outs[0], outs[1], shallow=False)
