@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--ref-len", type=int, default=50000)
     ap.add_argument("--band", type=int, default=50)
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = cores)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = 4 x cores, about 15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -311,7 +311,7 @@ def main():
                            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_max}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n = args.cpu_sample or cores
+            n = args.cpu_sample or 4 * cores
             idx = list(range(min(n, b.n)))
             dt, ccells, cops = cpu_realign_sample(b, idx, args.band, cores)
             for k, i in enumerate(idx):                          # the checker role: same CIGARs as the GPU path

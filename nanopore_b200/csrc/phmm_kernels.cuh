@@ -245,12 +245,17 @@ __device__ __forceinline__ double fold_logadd(const double *v, int n) {
 
 // Expectation updates of one cell: same transition enumeration as the forward
 // cell, p = exp(from + to + (eP + tP) - total), accumulated in 2^-32 fixed point.
+// Integer addition is associative, so the sums may be regrouped freely: the 15
+// transition counts stay in per-thread registers (accT, flushed once per region)
+// and the emission counts are first summed per target state (the symbols are
+// fixed for a cell), which leaves 5 shared-memory atomics per cell instead of 30.
+constexpr int EXP_NT = 15;   // accT slots: lower M>sX sX>sX sY>sX M>lX lX>lX | middle M sX sY lX lY >M | upper M>sY sY>sY sX>sY M>lY lY>lY
 template <bool SWITCH>
 __device__ __forceinline__ void expect_cell(const DevModel &m, const EmisTables &t,
                                             const double *F1, int xlo1, int w1,
                                             const double *F2, int xlo2, int w2,
                                             int x, int cX, int cY, const double B[NS], double total,
-                                            unsigned long long *sT, unsigned long long *sE) {
+                                            unsigned long long accT[EXP_NT], unsigned long long *sE) {
     const int jl = x - 1 - xlo1;
     const int ju = jl + 1;
     const int jm = x - 1 - xlo2;
@@ -259,41 +264,50 @@ __device__ __forceinline__ void expect_cell(const DevModel &m, const EmisTables 
     const bool okm = (unsigned)jm < (unsigned)w2;
     const bool emit = cX < 4 && cY < 4;
     const int ecol = cX * 4 + cY;
-#define PHMM_EXPECT(FROMV, F_, T_, EP)                                                          \
+    unsigned long long qE[NS] = {0ull, 0ull, 0ull, 0ull, 0ull};
+#define PHMM_EXPECT(SLOT, FROMV, F_, T_, EP)                                                    \
     do {                                                                                        \
         const double pr = exp_det((FROMV) + B[T_] + ((EP) + m.tr[(F_) * 5 + (T_)]) - total);   \
         const unsigned long long q = (unsigned long long)__double2ll_rd(pr * 4294967296.0);    \
-        if (q) {                                                                                \
-            atomicAdd(&sT[(F_) * 5 + (T_)], q);                                                 \
-            if (emit) atomicAdd(&sE[(T_) * 16 + ecol], q);                                      \
-        }                                                                                       \
+        accT[SLOT] += q;                                                                        \
+        qE[T_] += q;                                                                            \
     } while (0)
     if (okl) {
         const double eP = t.eX[cX];
-        PHMM_EXPECT(F1[jl], S_M, S_SX, eP);
-        PHMM_EXPECT(F1[w1 + jl], S_SX, S_SX, eP);
-        if (SWITCH) PHMM_EXPECT(F1[2 * w1 + jl], S_SY, S_SX, eP);
-        PHMM_EXPECT(F1[jl], S_M, S_LX, eP);
-        PHMM_EXPECT(F1[3 * w1 + jl], S_LX, S_LX, eP);
+        PHMM_EXPECT(0, F1[jl], S_M, S_SX, eP);
+        PHMM_EXPECT(1, F1[w1 + jl], S_SX, S_SX, eP);
+        if (SWITCH) PHMM_EXPECT(2, F1[2 * w1 + jl], S_SY, S_SX, eP);
+        PHMM_EXPECT(3, F1[jl], S_M, S_LX, eP);
+        PHMM_EXPECT(4, F1[3 * w1 + jl], S_LX, S_LX, eP);
     }
     if (okm) {
         const double eP = t.eM[cX * 5 + cY];
-        PHMM_EXPECT(F2[jm], S_M, S_M, eP);
-        PHMM_EXPECT(F2[w2 + jm], S_SX, S_M, eP);
-        PHMM_EXPECT(F2[2 * w2 + jm], S_SY, S_M, eP);
-        PHMM_EXPECT(F2[3 * w2 + jm], S_LX, S_M, eP);
-        PHMM_EXPECT(F2[4 * w2 + jm], S_LY, S_M, eP);
+        PHMM_EXPECT(5, F2[jm], S_M, S_M, eP);
+        PHMM_EXPECT(6, F2[w2 + jm], S_SX, S_M, eP);
+        PHMM_EXPECT(7, F2[2 * w2 + jm], S_SY, S_M, eP);
+        PHMM_EXPECT(8, F2[3 * w2 + jm], S_LX, S_M, eP);
+        PHMM_EXPECT(9, F2[4 * w2 + jm], S_LY, S_M, eP);
     }
     if (oku) {
         const double eP = t.eY[cY];
-        PHMM_EXPECT(F1[ju], S_M, S_SY, eP);
-        PHMM_EXPECT(F1[2 * w1 + ju], S_SY, S_SY, eP);
-        if (SWITCH) PHMM_EXPECT(F1[w1 + ju], S_SX, S_SY, eP);
-        PHMM_EXPECT(F1[ju], S_M, S_LY, eP);
-        PHMM_EXPECT(F1[4 * w1 + ju], S_LY, S_LY, eP);
+        PHMM_EXPECT(10, F1[ju], S_M, S_SY, eP);
+        PHMM_EXPECT(11, F1[2 * w1 + ju], S_SY, S_SY, eP);
+        if (SWITCH) PHMM_EXPECT(12, F1[w1 + ju], S_SX, S_SY, eP);
+        PHMM_EXPECT(13, F1[ju], S_M, S_LY, eP);
+        PHMM_EXPECT(14, F1[4 * w1 + ju], S_LY, S_LY, eP);
     }
 #undef PHMM_EXPECT
+    if (emit) {
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+            if (qE[s]) atomicAdd(&sE[s * 16 + ecol], qE[s]);
+    }
 }
+
+// accT slot -> transition index from*5+to
+__device__ __constant__ int EXP_SLOT_TR[EXP_NT] = {S_M * 5 + S_SX, S_SX * 5 + S_SX, S_SY * 5 + S_SX, S_M * 5 + S_LX, S_LX * 5 + S_LX,
+                                                   S_M * 5 + S_M, S_SX * 5 + S_M, S_SY * 5 + S_M, S_LX * 5 + S_M, S_LY * 5 + S_M,
+                                                   S_M * 5 + S_SY, S_SY * 5 + S_SY, S_SX * 5 + S_SY, S_M * 5 + S_LY, S_LY * 5 + S_LY};
 
 template <int NW, bool SWITCH, bool EXPECT>
 __global__ void __launch_bounds__(NW * 32) k_fwdbwd(const __grid_constant__ FbArgs a) {
@@ -333,6 +347,11 @@ __global__ void __launch_bounds__(NW * 32) k_fwdbwd(const __grid_constant__ FbAr
             for (int i = tid; i < 80; i += NT) sE[i] = 0ull;
         }
         double ll = 0.0;                              // thread 0 only
+        unsigned long long accT[EXPECT ? EXP_NT : 1];  // this thread's transition counts of the region
+        if (EXPECT) {
+#pragma unroll
+            for (int k = 0; k < EXP_NT; k++) accT[k] = 0ull;
+        }
         if (nd > 0) {
             BandIter it;
             it.init(a.runs + reg.run0, reg.nrun, lx, ly, e);
@@ -436,7 +455,7 @@ __global__ void __launch_bounds__(NW * 32) k_fwdbwd(const __grid_constant__ FbAr
                                     const int cX = x >= 1 ? X[x - 1] : 4;
                                     const int cY = y >= 1 ? Y[y - 1] : 4;
                                     expect_cell<SWITCH>(a.m, tab, fr + (int64_t)f1.off * NS, f1.xlo, f1.w,
-                                                        fr + (int64_t)f2.off * NS, f2.xlo, fw2, x, cX, cY, o, total, sT, sE);
+                                                        fr + (int64_t)f2.off * NS, f2.xlo, fw2, x, cX, cY, o, total, accT, sE);
                                 }
                             }
                         }
@@ -490,7 +509,7 @@ __global__ void __launch_bounds__(NW * 32) k_fwdbwd(const __grid_constant__ FbAr
                                     const int cX = x >= 1 ? X[x - 1] : 4;
                                     const int cY = y >= 1 ? Y[y - 1] : 4;
                                     expect_cell<SWITCH>(a.m, tab, fr + (int64_t)f1.off * NS, f1.xlo, f1.w,
-                                                        fr + (int64_t)f2.off * NS, f2.xlo, fw2, x, cX, cY, o, total, sT, sE);
+                                                        fr + (int64_t)f2.off * NS, f2.xlo, fw2, x, cX, cY, o, total, accT, sE);
                                 }
                             }
                         }
@@ -504,6 +523,11 @@ __global__ void __launch_bounds__(NW * 32) k_fwdbwd(const __grid_constant__ FbAr
                 off2 = off1; xlo2 = xlo1; w2 = w1;
                 off1 = off; xlo1 = xlo; w1 = w;
             }
+        }
+        if (EXPECT) {
+#pragma unroll
+            for (int k = 0; k < EXP_NT; k++)
+                if (accT[k]) atomicAdd(&sT[EXP_SLOT_TR[k]], accT[k]);
         }
         block_sync<NW>();
         if (tid == 0) {
