@@ -9,7 +9,9 @@ n = int(sys.argv[1])
 band = int(os.environ.get("BAND", "50"))
 L, R = int(os.environ.get("READ_LEN", "10000")), int(os.environ.get("REF_LEN", "50000"))
 gf = os.environ.get("GLOBAL_FORM", "1") == "1"
-b = synth.make_batch(n, L, R, seed=1001, global_form=gf)
+ch = dict(sub=float(os.environ.get("SUB", "0.05")), ins=float(os.environ.get("INS", "0.04")), dele=float(os.environ.get("DEL", "0.06")))
+lengths = synth.pareto_lengths(n, seed=5) if os.environ.get("PARETO") == "1" else None      # BASELINE.json configs[4] shape
+b = synth.make_batch(n, L, R, seed=1001, global_form=gf, lengths=lengths, **ch)
 for spec in sys.argv[2:] or [""]:
     ctx = capi.PhmmContext(0)
     for kv in [s for s in spec.split(",") if s]:
@@ -23,7 +25,7 @@ for spec in sys.argv[2:] or [""]:
         ctx.run()
         ts.append(ctx.stats()["ms_fwdbwd"])
     st = ctx.stats()
-    print("%-40s fwdbwd %9.2f ms  decode %7.2f ms  slots %4d  slotMB %7.1f  cells %.3e  -> %.1f Gcell/s  %.0f GB/s(80B/cell)" % (
+    print("%-40s fwdbwd %9.2f ms  decode %7.2f ms  slots %4d  slotMB %7.1f  cells %.3e  -> %.1f Gcell/s  %.0f GB/s(80B/cell)  regions %d  %.0f reads/s" % (
         spec or "(default)", min(ts), st["ms_decode"], st["n_slots"], st["slot_bytes"] / 1e6, st["cells"],
-        st["cells"] / min(ts) * 1e-6, 80.0 * st["cells"] / min(ts) * 1e-6), flush=True)
+        st["cells"] / min(ts) * 1e-6, 80.0 * st["cells"] / min(ts) * 1e-6, st["n_regions"], n / ((min(ts) + st["ms_decode"]) * 1e-3)), flush=True)
     ctx.close()
