@@ -61,6 +61,7 @@ struct BatchState {
     // windowed kernel (k_fb2)
     bool fast = false;
     std::vector<int64_t> tb_off;              // n_regions + 1
+    std::vector<int64_t> rec_off;             // n_regions + 1: first diagonal record of each region
     int64_t ring_doubles = 0; int32_t wcap = 0, wg = 0, tcap = 0;
     size_t fb2_smem = 0;
     phmm_batch_stats stats;
@@ -82,7 +83,7 @@ struct phmm_ctx {
     DevBuf d_ref; int64_t ref_len = -1;
     DevBuf d_reads, d_regions, d_runs, d_geom, d_order, d_counter;
     DevBuf d_fring, d_dtab, d_bring, d_dots;
-    DevBuf d_tboff, d_tbp, d_ring, d_wide, d_fsave, d_totals;
+    DevBuf d_tboff, d_tbp, d_ring, d_wide, d_fsave, d_totals, d_recs, d_recoff;
     DevBuf d_px, d_py, d_pw, d_npairs;
     DevBuf d_expT, d_expE, d_expLL;
     DevBuf d_sumx, d_sumy, d_dstart, d_dfill, d_sidx, d_wre, d_pred, d_colmap, d_sring, d_lring;
@@ -264,7 +265,7 @@ template <int NW, bool SW>
 int fb2_occupancy(size_t smem) {
     int n = 0;
     if (cudaFuncSetAttribute(k_fb2<NW, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fb2<NW, SW>, (NW + 1) * 32, smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fb2<NW, SW>, NW * 32, smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
     return n;
 }
 
@@ -275,9 +276,9 @@ int fb2_occupancy(int nw, bool sw, size_t smem) {
 }
 
 void fb2_launch(int nw, bool sw, const Fb2Args &a, int slots, size_t smem, cudaStream_t st) {
-    if (nw == 2) { if (sw) k_fb2<2, true><<<slots, 96, smem, st>>>(a); else k_fb2<2, false><<<slots, 96, smem, st>>>(a); }
-    else if (nw == 4) { if (sw) k_fb2<4, true><<<slots, 160, smem, st>>>(a); else k_fb2<4, false><<<slots, 160, smem, st>>>(a); }
-    else { if (sw) k_fb2<8, true><<<slots, 288, smem, st>>>(a); else k_fb2<8, false><<<slots, 288, smem, st>>>(a); }
+    if (nw == 2) { if (sw) k_fb2<2, true><<<slots, 64, smem, st>>>(a); else k_fb2<2, false><<<slots, 64, smem, st>>>(a); }
+    else if (nw == 4) { if (sw) k_fb2<4, true><<<slots, 128, smem, st>>>(a); else k_fb2<4, false><<<slots, 128, smem, st>>>(a); }
+    else { if (sw) k_fb2<8, true><<<slots, 256, smem, st>>>(a); else k_fb2<8, false><<<slots, 256, smem, st>>>(a); }
 }
 
 int32_t pow2_at_least(int32_t v) { int32_t p = 1; while (p < v) p <<= 1; return p; }
@@ -323,8 +324,7 @@ int plan_memory(phmm_ctx *ctx) {
     for (int64_t i = 0; i < nreg; i++) max_live_doubles = std::max(max_live_doubles, b.geom[i].max_live_doubles);
     // the windowed kernel needs a total-probability schedule that looks one traceback point ahead
     b.fast = !b.expect && !ctx->force_legacy && b.params.min_diags >= 2 * (b.params.tb_diags + 1) + 2 &&
-             b.params.min_diags - b.params.tb_diags - 1 > FB2_PRE + 2 &&     // the producer never runs two traceback points ahead
-             max_live_doubles + (FB2_PRE + 2) * 6 * (int64_t)b.bw + 16 < 0x7ffffff0;
+             max_live_doubles + 4 * 6 * (int64_t)b.bw + 16 < 0x7ffffff0;
     int occ = 1;
     int64_t slot_bytes = 0;
     if (b.fast) {
@@ -333,14 +333,17 @@ int plan_memory(phmm_ctx *ctx) {
         b.nw = ctx->opt_warps ? ctx->opt_warps : (avgw <= 48.0 ? 2 : (avgw <= 320.0 ? 4 : 8));
         b.wg = pow2_at_least(b.bw);
         b.wcap = ctx->opt_wcap ? ctx->opt_wcap : std::max<int32_t>(64, std::min<int32_t>(512, b.wg));
-        // the producer warp allocates FB2_PRE diagonals ahead of the compute warps
-        b.ring_doubles = max_live_doubles + (FB2_PRE + 2) * 6 * (int64_t)b.bw + 16;
-        b.dcap += FB2_PRE + 4;
+        // bump allocation with wrap-around wastes at most one diagonal's worth at the end of the ring
+        b.ring_doubles = max_live_doubles + 4 * 6 * (int64_t)b.bw + 16;
+        b.dcap += 4;
         b.tcap = b.dcap / TOTAL_EVERY + 4;
+        // one 16-byte record per diagonal of every region (k_records)
+        b.rec_off.assign(nreg + 1, 0);
+        for (int64_t i = 0; i < nreg; i++) b.rec_off[i + 1] = b.rec_off[i] + (int64_t)b.regions[i].lx + b.regions[i].ly + 1;
         b.fb2_smem = (size_t)2 * CS * b.wcap * 8 + FB2_TAB * 8 + 2 * FB2_RQ * sizeof(DiagRec);
         occ = fb2_occupancy(b.nw, sw, b.fb2_smem);
         if (occ < 1) return fail(ctx, PHMM_E_CUDA, "k_fb2 does not fit on this device");
-        slot_bytes = b.ring_doubles * 8 + (int64_t)b.dcap * sizeof(DiagRec) + (int64_t)4 * NS * b.wg * 8 +
+        slot_bytes = b.ring_doubles * 8 + (int64_t)4 * NS * b.wg * 8 +
                      (int64_t)2 * CS * b.wcap * 8 + ((int64_t)b.tcap + b.wg) * 8;
     } else {
         b.nw = avgw <= 40.0 ? 1 : (avgw <= 96.0 ? 2 : 4);
@@ -349,7 +352,8 @@ int plan_memory(phmm_ctx *ctx) {
     }
     int64_t want = (int64_t)ctx->sm_count * occ;
     // fixed allocations
-    const int64_t fixed = b.total_pair_cap * 12 + b.total_mrun_cap * 12 + nreg * (sizeof(Region) + sizeof(RegionGeom) + 64);
+    const int64_t fixed = b.total_pair_cap * 12 + b.total_mrun_cap * 12 + nreg * (sizeof(Region) + sizeof(RegionGeom) + 64) +
+                          (b.fast ? b.rec_off[nreg] * (int64_t)sizeof(DiagRec) + nreg * 8 : 0);
     const int64_t dec_slot_bytes = (int64_t)(b.max_lx + 1) * 4 + (int64_t)(b.max_ly + 1) * 4 + (int64_t)(b.max_nd + 4) * 8 +
                                    (int64_t)(b.max_pairs + 1) * 16 + (int64_t)2 * (b.max_lx + 2) * 8 + (int64_t)3 * b.bw * 12;
     int64_t avail = budget(ctx) - fixed;
@@ -363,15 +367,17 @@ int plan_memory(phmm_ctx *ctx) {
     b.fb_slots = (int)want; b.dec_slots = (int)dec_want;
     b.stats.slot_bytes = slot_bytes; b.stats.n_slots = want;
 
-    CK(ctx->d_dtab.ensure((size_t)want * b.dcap * sizeof(DiagRec)));
     if (b.fast) {
-        ctx->d_fring.release(); ctx->d_bring.release(); ctx->d_dots.release();
+        ctx->d_fring.release(); ctx->d_bring.release(); ctx->d_dots.release(); ctx->d_dtab.release();
+        CK(ctx->d_recs.ensure((size_t)b.rec_off[nreg] * sizeof(DiagRec) + 64));
+        CK(ctx->d_recoff.ensure((size_t)(nreg + 1) * 8));
         CK(ctx->d_ring.ensure((size_t)want * b.ring_doubles * 8));
         CK(ctx->d_wide.ensure((size_t)want * 4 * NS * b.wg * 8));
         CK(ctx->d_fsave.ensure((size_t)want * 2 * CS * b.wcap * 8));
         CK(ctx->d_totals.ensure((size_t)want * ((size_t)b.tcap + b.wg) * 8));
     } else {
-        ctx->d_ring.release(); ctx->d_wide.release();
+        ctx->d_ring.release(); ctx->d_wide.release(); ctx->d_recs.release();
+        CK(ctx->d_dtab.ensure((size_t)want * b.dcap * sizeof(DiagRec)));
         CK(ctx->d_fring.ensure((size_t)want * b.ring_cells * NS * 8));
         CK(ctx->d_bring.ensure((size_t)want * 3 * b.bw * NS * 8));
         CK(ctx->d_dots.ensure((size_t)want * 2 * b.bw * 8));
@@ -403,6 +409,15 @@ int plan_memory(phmm_ctx *ctx) {
     }
     // regions carry the plan (pair_off, caps): upload
     CK(cudaMemcpyAsync(ctx->d_regions.p, b.regions.data(), nreg * sizeof(Region), cudaMemcpyHostToDevice, ctx->stream));
+    if (b.fast) {
+        // diagonal records of every region (data independent; once per prepared batch)
+        CK(cudaMemcpyAsync(ctx->d_recoff.p, b.rec_off.data(), (size_t)(nreg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        k_records<<<(unsigned)((nreg + 63) / 64), 64, 0, ctx->stream>>>(
+            ctx->d_regions.as<Region>(), ctx->d_runs.as<Run>(), (int)nreg, b.dp, ctx->d_tboff.as<int64_t>(), ctx->d_tbp.as<int32_t>(),
+            reinterpret_cast<const int32_t *>(ctx->d_geom.as<char>() + offsetof(RegionGeom, tracebacks)), (int)(sizeof(RegionGeom) / 4),
+            b.ring_doubles, b.wcap, ctx->d_recoff.as<int64_t>(), ctx->d_recs.as<DiagRec>());
+        CK(cudaGetLastError());
+    }
     return PHMM_OK;
 }
 
@@ -492,7 +507,7 @@ int do_run(phmm_ctx *ctx) {
     BatchState &b = ctx->b;
     if (!b.prepared) return fail(ctx, PHMM_E_STATE, "no batch prepared");
     const int64_t nreg = (int64_t)b.regions.size();
-    b.stats.launches = 1;   // geometry
+    b.stats.launches = b.fast ? 2 : 1;   // geometry (+ diagonal records)
     b.stats.run_launches = 0;
     if (nreg == 0) { b.ran = true; return PHMM_OK; }
     CK(cudaSetDevice(ctx->device));
@@ -520,7 +535,7 @@ int do_run(phmm_ctx *ctx) {
         f2.ntb = reinterpret_cast<const int32_t *>(ctx->d_geom.as<char>() + offsetof(RegionGeom, tracebacks));
         f2.ntb_stride = (int32_t)(sizeof(RegionGeom) / 4);
         f2.ring = ctx->d_ring.as<double>(); f2.ring_doubles = b.ring_doubles;
-        f2.dtab = ctx->d_dtab.as<DiagRec>(); f2.dcap = b.dcap;
+        f2.recs = ctx->d_recs.as<DiagRec>(); f2.rec_off = ctx->d_recoff.as<int64_t>();
         f2.wide = ctx->d_wide.as<double>(); f2.wg = b.wg;
         f2.fsave = ctx->d_fsave.as<double>(); f2.totals = ctx->d_totals.as<double>(); f2.tcap = b.tcap;
         f2.wcap = b.wcap;

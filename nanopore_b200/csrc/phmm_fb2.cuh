@@ -1,18 +1,19 @@
 // phmm_fb2.cuh -- k_fb2: the windowed forward / backward / posterior kernel of the realignment path.
 //
-// One thread block per DP region (work queue, longest first): NW compute warps + 1 producer warp.
+// One thread block per DP region (work queue, longest first), NW warps, all of them computing cells.
 //
-// Compute warps.  Per anti-diagonal each thread owns one cell (x = xlo + tid, + NC, ...).  The two
-// previous diagonals live in shared memory as [column][5 states] and are updated in place: cell (d, x)
-// sits in column (x - (d >> 1)) & mask of the buffer of parity d & 1, which is exactly the column of its
-// `middle` predecessor (d-2, x-1), read by the same thread just before it is overwritten.  Diagonals
-// wider than the shared-memory buffer fall back to a global buffer of the same shape.
+// Per anti-diagonal each thread owns the cells of its columns.  The two previous diagonals live in shared memory as
+// [column][5 states] and are updated in place: cell (d, x) sits in column (x - (d >> 1)) & mask of the buffer of
+// parity d & 1, which is exactly the column of its `middle` predecessor (d-2, x-1), read by the same thread just
+// before it is overwritten.  Diagonals wider than the shared-memory buffer fall back to a global buffer of the
+// same shape.
 //
-// Producer warp.  Walks the band geometry (anchor runs -> first x and width of every diagonal), allocates
-// the diagonal's space in the HBM ring, decides whether the window will evaluate the total probability on
-// it, and publishes that record a few diagonals ahead through a shared-memory FIFO; on the way back it
-// prefetches the records of the live window from HBM into the same kind of FIFO.  The compute warps read
-// one 16-byte record per diagonal instead of re-deriving the geometry 256 times.
+// Diagonal records.  The band geometry (first x and width of every diagonal), the diagonal's slot in the HBM ring,
+// whether the window evaluates the total probability on it and whether it may take the unguarded fast path are
+// data independent: k_records (one thread per region, run once per prepared batch) writes one 16-byte record per
+// diagonal to HBM, and the first warp of each block streams them 32 at a time into a shared-memory FIFO, two
+// batches ahead (the load of one batch is consumed a batch later, so nobody waits for it).  No thread of the hot
+// kernel re-derives geometry.
 //
 // HBM holds, per live diagonal, only what a later phase needs (the "ring", recycled per traceback window):
 //     F_M, overwritten by F_M + B_M on the way back   every diagonal       -> posterior, step-over term of the total
@@ -33,17 +34,15 @@
 
 namespace phmm {
 
-constexpr int FB2_RQ = 32;          // record FIFO entries (power of two)
-constexpr int FB2_BATCH = 8;        // the producer warp meets the compute warps at a block barrier every FB2_BATCH diagonals
-constexpr int FB2_AHEAD = 16;       // records ready beyond the current diagonal at such a meeting
-constexpr int FB2_PRE = FB2_AHEAD + FB2_BATCH;   // furthest the producer runs ahead (<= FB2_RQ - FB2_BATCH)
+constexpr int FB2_RQ = 64;          // record FIFO entries (power of two): two batches
+constexpr int FB2_BATCH = 32;       // records streamed per refill (one per lane of the first warp)
 constexpr int REC_TOT = 1;          // DiagRec::pad bits: the window evaluates the total probability here
 constexpr int REC_WIDE = 2;         //   wider than the shared-memory buffer: lives in the global fallback buffer
 constexpr int REC_FAST3 = 4;        //   diagonals d-2, d-1, d (+-1 column) fit the shared-memory columns without aliasing
 #ifndef PHMM_CS
-#define PHMM_CS 6
+#define PHMM_CS 5
 #endif
-constexpr int CS = PHMM_CS;               // doubles per shared-memory column: 5 states + 1 pad (16-byte aligned vector loads)
+constexpr int CS = PHMM_CS;               // doubles per shared-memory column: 5 (five resident regions per SM at 512 columns) or 6 (padded: 16-byte loads)
 constexpr int FB2_TAB = 16 + 25 * CS + 5 * CS + 5 * CS;   // logAdd coefficients + the three (emission + transition) tables
 
 struct Fb2Args {
@@ -62,7 +61,8 @@ struct Fb2Args {
     int32_t ntb_stride;          // in int32 units
     // per-slot scratch (slot = blockIdx.x)
     double *ring;   int64_t ring_doubles;
-    DiagRec *dtab;  int32_t dcap;
+    const DiagRec *recs;         // records of region r: recs[rec_off[r] + d], d = 1 .. lx + ly
+    const int64_t *rec_off;
     double *wide;   int32_t wg;  // 4 x wg x 5 doubles: F even/odd, B even/odd for diagonals wider than wcap
     double *fsave;               // 2 x wcap x CS doubles: forward state across a traceback window
     double *totals; int32_t tcap; // per slot: tcap totals, then wg sums F_M + B_M of the diagonal just above the posterior range
@@ -216,9 +216,6 @@ __device__ __forceinline__ void bwd_cell3(const Tabs &t, const double *pl, bool 
     }
 }
 
-// barrier of the compute warps only (the producer warp runs ahead between block barriers)
-__device__ __forceinline__ void bar_compute(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
-
 // left-to-right logAdd fold of n values produced by f(i), starting from -inf (dpDiagonal_dotProduct order)
 template <typename F>
 __device__ __forceinline__ double fold_seq(int n, const char *ctab, F f) {
@@ -227,43 +224,35 @@ __device__ __forceinline__ double fold_seq(int n, const char *ctab, F f) {
     return t;
 }
 
-// Producer lane state (shared memory, touched by one thread): band walk, ring allocator, schedule of
-// total-probability diagonals (needs the next two traceback points), column extent of the last two diagonals.
-struct ProdState {
+// ---------------------------------------------------------------------------
+// k_records: one thread per region walks the band once and writes the diagonal records of the whole region.
+// Ring slots are handed out by a bump allocator that wraps; the ring is sized (host) for the largest live window.
+// The schedule of total-probability diagonals needs the traceback points (k_geometry): every TOTAL_EVERY-th
+// diagonal counted down from the first posterior diagonal of the window the diagonal belongs to.
+// ---------------------------------------------------------------------------
+__global__ void k_records(const Region *regions, const Run *runs, int n_regions, DevParams p, const int64_t *tb_off,
+                          const int32_t *tbp, const int32_t *ntb, int ntb_stride, int64_t ring_doubles, int wcap,
+                          const int64_t *rec_off, DiagRec *recs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_regions) return;
+    const Region reg = regions[r];
+    const int nd = reg.lx + reg.ly;
+    if (nd == 0) return;
+    const int32_t *tb = tbp + tb_off[r];
+    const int ntbr = ntb[(int64_t)r * ntb_stride];
+    const int tbd = p.tb_diags + 1;
+    DiagRec *out = recs + rec_off[r];
     BandIter it;
-    int d;                      // last diagonal generated
-    int roff, rsz;              // ring entry of that diagonal
-    int tk, P, TF, Pn, TFn;
-    int c1lo, c1hi, c2lo, c2hi; // columns (x - (d >> 1)) of diagonals d and d-1; empty: lo > hi
-    int wf1, wf2;               // their REC_WIDE bits
-};
-
-__device__ __noinline__ void fb2_produce_init(ProdState *ps, const Run *runs, int nrun, int lx, int ly, int expansion,
-                                              const int32_t *tb, int ntb, int tbd) {
-    const int nd = lx + ly;
-    BandIter it;
-    it.init(runs, nrun, lx, ly, expansion);
-    ps->it = it;
-    ps->d = 0; ps->roff = 0; ps->rsz = 0; ps->tk = 0;
-    const int P = tb[0];
-    ps->P = P;
-    ps->TF = P - (P == nd ? 0 : tbd);
-    const int Pn = ntb > 1 ? tb[1] : nd;
-    ps->Pn = Pn;
-    ps->TFn = Pn - (Pn == nd ? 0 : tbd);
-    ps->c1lo = 0; ps->c1hi = 0;                 // diagonal 0: the single cell (0,0), column 0
-    ps->c2lo = 1; ps->c2hi = 0;                 // no diagonal -1
-    ps->wf1 = 0; ps->wf2 = 0;
-}
-
-// generates the records of the next `count` diagonals (stops at nd)
-__device__ __noinline__ void fb2_produce(ProdState *ps, int count, int nd, const int32_t *tb, int ntb, int tbd,
-                                         int64_t ring_doubles, int wcap, DiagRec *srec, DiagRec *dt, int dcap) {
-    BandIter it = ps->it;
-    int d = ps->d, roff = ps->roff, rsz = ps->rsz, tk = ps->tk, P = ps->P, TF = ps->TF, Pn = ps->Pn, TFn = ps->TFn;
-    int c1lo = ps->c1lo, c1hi = ps->c1hi, c2lo = ps->c2lo, c2hi = ps->c2hi, wf1 = ps->wf1, wf2 = ps->wf2;
-    for (int k = 0; k < count && d < nd; k++) {
-        d++;
+    it.init(runs + reg.run0, reg.nrun, reg.lx, reg.ly, p.expansion);
+    int roff = 0, rsz = 0, tk = 0;
+    int P = tb[0];
+    int TF = P - (P == nd ? 0 : tbd);
+    int Pn = ntbr > 1 ? tb[1] : nd;
+    int TFn = Pn - (Pn == nd ? 0 : tbd);
+    int c1lo = 0, c1hi = 0;                     // diagonal 0: the single cell (0,0), column 0
+    int c2lo = 1, c2hi = 0;                     // no diagonal -1
+    int wf1 = 0, wf2 = 0;
+    for (int d = 1; d <= nd; d++) {
         int xlo, w;
         it.diag(d, xlo, w);
         const int tf = d <= TF ? TF : TFn;
@@ -275,44 +264,46 @@ __device__ __noinline__ void fb2_produce(ProdState *ps, int count, int nd, const
         if (d == P) {
             tk++;
             P = Pn; TF = TFn;
-            Pn = tk + 1 < ntb ? tb[tk + 1] : nd;
+            Pn = tk + 1 < ntbr ? tb[tk + 1] : nd;
             TFn = Pn - (Pn == nd ? 0 : tbd);
         }
+        // columns (x - (d >> 1)) of this and the two previous diagonals, one spare either side: do they alias?
         const int clo = xlo - (d >> 1), chi = clo + w - 1;
         const int wf = w > wcap ? REC_WIDE : 0;
         int lo = min(clo, c1lo), hi = max(chi, c1hi);
         if (c2lo <= c2hi) { lo = min(lo, c2lo); hi = max(hi, c2hi); }
         const bool fast3 = !(wf | wf1 | wf2) && (hi - lo + 3 <= wcap);
         DiagRec rc; rc.off = off; rc.xlo = xlo; rc.w = w; rc.pad = (tot ? REC_TOT : 0) | wf | (fast3 ? REC_FAST3 : 0);
-        srec[d & (FB2_RQ - 1)] = rc;
-        dt[d % dcap] = rc;
+        out[d] = rc;
         c2lo = c1lo; c2hi = c1hi; wf2 = wf1;
         c1lo = clo; c1hi = chi; wf1 = wf;
     }
-    ps->it = it;
-    ps->d = d; ps->roff = roff; ps->rsz = rsz; ps->tk = tk; ps->P = P; ps->TF = TF; ps->Pn = Pn; ps->TFn = TFn;
-    ps->c1lo = c1lo; ps->c1hi = c1hi; ps->c2lo = c2lo; ps->c2hi = c2hi; ps->wf1 = wf1; ps->wf2 = wf2;
+}
+
+__device__ __forceinline__ DiagRec ld_rec(const DiagRec *p) {
+    const int4 v = *reinterpret_cast<const int4 *>(p);
+    DiagRec r; r.off = v.x; r.xlo = v.y; r.w = v.z; r.pad = v.w;
+    return r;
 }
 
 #ifndef PHMM_MB4
-#define PHMM_MB4 4
+#define PHMM_MB4 5
 #endif
-constexpr int fb2_min_blocks(int nw) { return nw == 8 ? 2 : (nw == 4 ? PHMM_MB4 : 6); }
+constexpr int fb2_min_blocks(int nw) { return nw == 8 ? 2 : (nw == 4 ? PHMM_MB4 : 8); }
 
 // Shared-memory diagonal buffers.  Cell (d, x) lives in column (x - (d >> 1)) & (wcap - 1) of the buffer of parity
 // d & 1, so a cell overwrites its own `middle` predecessor (d-2, x-1) and its `lower` / `upper` predecessors sit in
 // the same and the adjacent column of the other buffer.  INVARIANT kept for both buffers: every column that is not
 // in the band of the diagonal the buffer currently holds contains -inf.  With it the recurrences read their
 // neighbours without any in-band test, whatever the band does at its ends, as long as the columns of three
-// consecutive diagonals (plus one either side) do not alias modulo wcap (REC_FAST3, decided by the producer).
+// consecutive diagonals (plus one either side) do not alias modulo wcap (REC_FAST3, decided by k_records).
 // Other diagonals take the guarded path and then restore the invariant by clearing every out-of-band column.
 template <int NW, bool SWITCH>
-__global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const __grid_constant__ Fb2Args a) {
-    constexpr int NC = NW * 32;            // compute threads
-    constexpr int NTA = NC + 32;           // + producer warp
+__global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW)) k_fb2(const __grid_constant__ Fb2Args a) {
+    constexpr int NC = NW * 32;            // threads; all compute
+    constexpr int NTA = NC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
-    const bool producer = tid >= NC;
     const int wcap = a.wcap, cmask = wcap - 1;
     double *const sbuf = reinterpret_cast<double *>(smem_raw);                  // [2][wcap][CS]
     double *const sct = sbuf + 2 * CS * wcap;                                    // 4 rows x (c3 c2 c1 c0)
@@ -320,7 +311,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
     DiagRec *const srec = reinterpret_cast<DiagRec *>(sct + FB2_TAB);            // [2][FB2_RQ]
     __shared__ int s_region;
     __shared__ int s_npairs;
-    __shared__ ProdState s_prod;
 
     if (tid == 0) {
         sct[0] = -0.009350833524763; sct[1] = 0.130659527668286; sct[2] = 0.498799810682272; sct[3] = 0.693203116424741;
@@ -345,7 +335,6 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
 
     const int slot = blockIdx.x;
     double *const ring = a.ring + (int64_t)slot * a.ring_doubles;
-    DiagRec *const dt = a.dtab + (int64_t)slot * a.dcap;
     double *const wide = a.wide + (int64_t)slot * 4 * NS * a.wg;
     double *const fsave = a.fsave + (int64_t)slot * 2 * CS * wcap;
     double *const totals = a.totals + (int64_t)slot * (a.tcap + a.wg);
@@ -384,9 +373,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
         if (nd > 0) {
             const int32_t *tb = a.tbp + a.tb_off[ridx];
             const int ntb = a.ntb[(int64_t)ridx * a.ntb_stride];
-            if (tid == NC) {
-                fb2_produce_init(&s_prod, a.runs + reg.run0, reg.nrun, lx, ly, a.p.expansion, tb, ntb, tbd);
-                fb2_produce(&s_prod, FB2_AHEAD, nd, tb, ntb, tbd, a.ring_doubles, wcap, srec, dt, a.dcap);
+            const DiagRec *const rec = a.recs + a.rec_off[ridx];
+            DiagRec pre;                                             // lanes of warp 0: record in flight for the batch after next
+            pre.off = pre.xlo = pre.w = pre.pad = 0;
+            if (tid < FB2_BATCH) {
+                if (1 + tid <= nd) srec[(1 + tid) & (FB2_RQ - 1)] = ld_rec(rec + 1 + tid);
+                if (1 + FB2_BATCH + tid <= nd) pre = ld_rec(rec + 1 + FB2_BATCH + tid);
             }
             // both buffers -inf, then diagonal 0: the single cell (0,0), column 0 of the even buffer
             for (int i = tid; i < 2 * CS * wcap; i += NTA) sbuf[i] = PHMM_NEG_INF;
@@ -404,17 +396,17 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
             int P = tb[0];
             __syncthreads();
             for (int d = 1; d <= nd; d++) {
-                if (((d - 1) & (FB2_BATCH - 1)) == 0) {
-                    // records up to d + FB2_AHEAD - 1 are published; the producer goes on with the next FB2_BATCH
-                    __syncthreads();
-                    if (tid == NC) fb2_produce(&s_prod, FB2_BATCH, nd, tb, ntb, tbd, a.ring_doubles, wcap, srec, dt, a.dcap);
+                if (((d - 1) & (FB2_BATCH - 1)) == 0 && tid < FB2_BATCH) {
+                    // records d .. d+31 are in the FIFO; publish d+32 .. d+63 (loaded a batch ago), fetch d+64 .. d+95
+                    if (d + FB2_BATCH + tid <= nd) srec[(d + FB2_BATCH + tid) & (FB2_RQ - 1)] = pre;
+                    if (d + 2 * FB2_BATCH + tid <= nd) pre = ld_rec(rec + d + 2 * FB2_BATCH + tid);
                 }
                 const DiagRec rc = srec[d & (FB2_RQ - 1)];
                 const int xlo = rc.xlo, w = rc.w;
                 const int h0 = d >> 1, par = d & 1;
                 const int clo = xlo - h0;                             // first column of this diagonal (unwrapped)
                 const bool fast = (rc.pad & REC_FAST3) != 0;
-                if (!producer) {
+                {
                     const bool tot = (rc.pad & REC_TOT) != 0;
                     double *const rg = ring + rc.off;
                     if (a.dbg & 32) {
@@ -468,7 +460,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                         }
                     }
                 }
-                if (!producer) {
+                {
                     if (fast) {
                         // columns of diagonal d-2 that left the band: back to -inf (nobody reads them during d)
                         if (w2 > 0) {
@@ -481,14 +473,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                         // are outside the band, and the only column of this buffer a cell reads is its own)
                         clear_outside(par, clo, w, tid, NC);
                     }
-                    bar_compute(NC);
+                    __syncthreads();
                 }
                 if (d == P && (a.dbg & 16)) {
                     traced_to = d - (d == nd ? 0 : tbd);
                     tk++;
                     P = tk < ntb ? tb[tk] : nd + 1;
                 } else if (d == P) {
-                    __syncthreads();            // the producer warp joins for the traceback window
                     // ------------------------- traceback window (traced_to, d] -------------------------
                     const bool at_end = d == nd;
                     const int traced_from = d - (at_end ? 0 : tbd);
@@ -497,9 +488,11 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                     if (!at_end) {
                         for (int i = tid; i < 2 * CS * wcap; i += NTA) fsave[i] = sbuf[i];
                     }
-                    if (producer && tid - NC < FB2_AHEAD) {
-                        const int dd = d - (tid - NC);
-                        if (dd > traced_to) srb[dd & (FB2_RQ - 1)] = dt[dd % a.dcap];
+                    DiagRec preb;                                                        // backward counterpart of `pre`
+                    preb.off = preb.xlo = preb.w = preb.pad = 0;
+                    if (tid < FB2_BATCH) {
+                        if (d - tid >= 1) srb[(d - tid) & (FB2_RQ - 1)] = ld_rec(rec + d - tid);
+                        if (d - FB2_BATCH - tid >= 1) preb = ld_rec(rec + d - FB2_BATCH - tid);
                     }
                     __syncthreads();
                     // the backward sweep reuses the two buffers: all -inf before its first diagonal
@@ -509,19 +502,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                     {
                         int bxlo1 = 0, bw1 = 0, bf1 = 0, bxlo2 = 0, bw2 = 0, bf2 = 0;      // diagonals dd+1, dd+2
                         for (int dd = d; dd > traced_to; dd--) {
-                            if (((d - dd) & (FB2_BATCH - 1)) == 0) {
-                                if (dd != d) __syncthreads();
-                                if (producer && tid - NC < FB2_BATCH) {           // records dd-16 .. dd-23 for the batch after next
-                                    const int dn = dd - FB2_AHEAD - (tid - NC);
-                                    if (dn > traced_to) srb[dn & (FB2_RQ - 1)] = dt[dn % a.dcap];
-                                }
+                            if (((d - dd) & (FB2_BATCH - 1)) == 0 && tid < FB2_BATCH) {
+                                if (dd - FB2_BATCH - tid >= 1) srb[(dd - FB2_BATCH - tid) & (FB2_RQ - 1)] = preb;
+                                if (dd - 2 * FB2_BATCH - tid >= 1) preb = ld_rec(rec + dd - 2 * FB2_BATCH - tid);
                             }
                             const DiagRec rb = srb[dd & (FB2_RQ - 1)];
                             const int hb0 = dd >> 1, bpar = dd & 1;
                             const int bclo = rb.xlo - hb0;
                             // fast: diagonals dd, dd+1, dd+2 are a FAST3 triple (flag of dd+2) and all exist
                             const bool bfast = dd + 2 <= d && (bf2 & REC_FAST3) != 0;
-                            if (!producer) {
+                            {
                                 double *const rg = ring + rb.off;
                                 const bool dots = (rb.pad & REC_TOT) != 0 && dd <= traced_from;
                                 if (a.dbg & 256) {
@@ -587,7 +577,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                                     }
                                 }
                             }
-                            if (!producer) {
+                            {
                                 if (bfast) {
                                     const int clo2 = bxlo2 - hb0 - 1, chi2 = clo2 + bw2 - 1, chi = bclo + rb.w - 1;
                                     clear_cols(bpar, clo2, min(bclo - 1, chi2), tid, NC);
@@ -595,22 +585,21 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                                 } else if (!(rb.pad & REC_WIDE)) {
                                     clear_outside(bpar, bclo, rb.w, tid, NC);
                                 }
-                                bar_compute(NC);
+                                __syncthreads();
                             }
                             bxlo2 = bxlo1; bw2 = bw1; bf2 = bf1;
                             bxlo1 = rb.xlo; bw1 = rb.w; bf1 = rb.pad;
                         }
                     }
-                    __syncthreads();
                     // phase 2: total probabilities, one thread per total diagonal
                     const int nk = traced_from > traced_to ? (traced_from - traced_to - 1) / TOTAL_EVERY + 1 : 0;
                     for (int k = tid; k < ((a.dbg & 64) ? 0 : nk); k += NTA) {
                         const int dd = traced_from - TOTAL_EVERY * k;
-                        const DiagRec r0 = dt[dd % a.dcap];
+                        const DiagRec r0 = rec[dd];
                         const double *cd = ring + r0.off + 5 * r0.w;
                         double total = fold_seq(r0.w, ctab, [&](int i) { return cd[i]; });
                         if (dd < d) {
-                            const DiagRec r1 = dt[(dd + 1) % a.dcap];
+                            const DiagRec r1 = rec[dd + 1];
                             const double *sm = dd + 1 > traced_from ? ovs : ring + r1.off;
                             const double t1 = fold_seq(r1.w, ctab, [&](int i) { return sm[i]; });
                             total = logadd_t(total, t1, ctab);
@@ -619,8 +608,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, fb2_min_blocks(NW)) k_fb2(const
                     }
                     __syncthreads();
                     // phase 3: posterior match probabilities, one warp per diagonal
-                    for (int dd = traced_from - (tid >> 5); dd > ((a.dbg & 128) ? traced_from : traced_to); dd -= NW + 1) {
-                        const DiagRec r0 = dt[dd % a.dcap];
+                    for (int dd = traced_from - (tid >> 5); dd > ((a.dbg & 128) ? traced_from : traced_to); dd -= NW) {
+                        const DiagRec r0 = rec[dd];
                         const double total = totals[(traced_from - dd) / TOTAL_EVERY];
                         const double *sm = ring + r0.off;
                         for (int i0 = tid & 31; i0 < r0.w; i0 += 128) {
