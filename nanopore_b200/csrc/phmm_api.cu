@@ -358,7 +358,8 @@ int plan_memory(phmm_ctx *ctx) {
                                    (int64_t)(b.max_pairs + 1) * 16 + (int64_t)2 * (b.max_lx + 2) * 8 + (int64_t)3 * b.bw * 12;
     int64_t avail = budget(ctx) - fixed;
     if (avail < slot_bytes + dec_slot_bytes) return fail(ctx, PHMM_E_NOMEM, "memory budget too small for one region of this batch");
-    int64_t dec_want = (int64_t)ctx->sm_count * 8;
+    // measured (profiles/r01b_phase_breakdown.txt, tune15): 2-warp decode blocks, 16 per SM, beat 4 warps x 8
+    int64_t dec_want = (int64_t)ctx->sm_count * (b.nw >= 2 ? 16 : 8);
     dec_want = std::min<int64_t>(dec_want, nreg);
     dec_want = std::max<int64_t>(1, std::min<int64_t>(dec_want, (avail / 4) / dec_slot_bytes));
     avail -= dec_want * dec_slot_bytes;
@@ -566,8 +567,7 @@ int do_run(phmm_ctx *ctx) {
         da.mrx = ctx->d_mrx.as<int32_t>(); da.mry = ctx->d_mry.as<int32_t>(); da.mrn = ctx->d_mrn.as<int32_t>();
         da.nmruns = ctx->d_nmruns.as<int32_t>(); da.score = ctx->d_score.as<int64_t>();
         if (b.nw == 1) k_decode<1><<<b.dec_slots, 32, 0, ctx->stream>>>(da);
-        else if (b.nw == 2) k_decode<2><<<b.dec_slots, 64, 0, ctx->stream>>>(da);
-        else k_decode<4><<<b.dec_slots, 128, 0, ctx->stream>>>(da);          // also for the 8-warp forward/backward class
+        else k_decode<2><<<b.dec_slots, 64, 0, ctx->stream>>>(da);
         CK(cudaGetLastError());
         b.stats.launches++; b.stats.run_launches++;
     }
