@@ -162,7 +162,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample or cores
+    sample = args.cpu_sample or 4 * cores          # 4 reads per thread: keeps the threads busy to the end of a step
     a2 = argparse.Namespace(**vars(args))
     a2.reads = sample * (args.steps + args.warmup)
     b = make_workload(a2, 0)

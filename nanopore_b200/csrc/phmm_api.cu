@@ -63,6 +63,7 @@ struct BatchState {
     std::vector<int64_t> tb_off;              // n_regions + 1
     std::vector<int64_t> rec_off;             // n_regions + 1: first diagonal record of each region
     int64_t ring_doubles = 0; int32_t wcap = 0, wg = 0, tcap = 0;
+    int32_t cell_doubles = 1, total_extra = 5;   // ring doubles per cell / extra on total-probability diagonals
     size_t fb2_smem = 0;
     phmm_batch_stats stats;
 };
@@ -261,25 +262,36 @@ int occupancy_fwdbwd(bool sw, bool expect) {
     return n > 0 ? n : 1;
 }
 
-template <int NW, bool SW>
-int fb2_occupancy(size_t smem) {
+template <int NW, bool SW, bool EX>
+int fb2_occupancy_t(size_t smem) {
     int n = 0;
-    if (cudaFuncSetAttribute(k_fb2<NW, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fb2<NW, SW>, NW * 32, smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    if (cudaFuncSetAttribute(k_fb2<NW, SW, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fb2<NW, SW, EX>, NW * 32, smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
     return n;
 }
 
-int fb2_occupancy(int nw, bool sw, size_t smem) {
-    if (nw == 2) return sw ? fb2_occupancy<2, true>(smem) : fb2_occupancy<2, false>(smem);
-    if (nw == 4) return sw ? fb2_occupancy<4, true>(smem) : fb2_occupancy<4, false>(smem);
-    return sw ? fb2_occupancy<8, true>(smem) : fb2_occupancy<8, false>(smem);
+template <int NW, bool SW, bool EX>
+int fb2_launch_t(const Fb2Args &a, int slots, size_t smem, cudaStream_t st) {
+    k_fb2<NW, SW, EX><<<slots, NW * 32, smem, st>>>(a);
+    return 0;
 }
 
-void fb2_launch(int nw, bool sw, const Fb2Args &a, int slots, size_t smem, cudaStream_t st) {
-    if (nw == 2) { if (sw) k_fb2<2, true><<<slots, 64, smem, st>>>(a); else k_fb2<2, false><<<slots, 64, smem, st>>>(a); }
-    else if (nw == 4) { if (sw) k_fb2<4, true><<<slots, 128, smem, st>>>(a); else k_fb2<4, false><<<slots, 128, smem, st>>>(a); }
-    else { if (sw) k_fb2<8, true><<<slots, 256, smem, st>>>(a); else k_fb2<8, false><<<slots, 256, smem, st>>>(a); }
-}
+#define FB2_DISPATCH(FN, ...)                                                                        \
+    do {                                                                                             \
+        if (nw == 2) {                                                                               \
+            if (ex) return sw ? FN<2, true, true>(__VA_ARGS__) : FN<2, false, true>(__VA_ARGS__);    \
+            return sw ? FN<2, true, false>(__VA_ARGS__) : FN<2, false, false>(__VA_ARGS__);          \
+        }                                                                                            \
+        if (nw == 4) {                                                                               \
+            if (ex) return sw ? FN<4, true, true>(__VA_ARGS__) : FN<4, false, true>(__VA_ARGS__);    \
+            return sw ? FN<4, true, false>(__VA_ARGS__) : FN<4, false, false>(__VA_ARGS__);          \
+        }                                                                                            \
+        if (ex) return sw ? FN<8, true, true>(__VA_ARGS__) : FN<8, false, true>(__VA_ARGS__);        \
+        return sw ? FN<8, true, false>(__VA_ARGS__) : FN<8, false, false>(__VA_ARGS__);              \
+    } while (0)
+
+int fb2_occupancy(int nw, bool sw, bool ex, size_t smem) { FB2_DISPATCH(fb2_occupancy_t, smem); }
+int fb2_launch(int nw, bool sw, bool ex, const Fb2Args &a, int slots, size_t smem, cudaStream_t st) { FB2_DISPATCH(fb2_launch_t, a, slots, smem, st); }
 
 int32_t pow2_at_least(int32_t v) { int32_t p = 1; while (p < v) p <<= 1; return p; }
 
@@ -323,8 +335,11 @@ int plan_memory(phmm_ctx *ctx) {
     int64_t max_live_doubles = 0;
     for (int64_t i = 0; i < nreg; i++) max_live_doubles = std::max(max_live_doubles, b.geom[i].max_live_doubles);
     // the windowed kernel needs a total-probability schedule that looks one traceback point ahead
-    b.fast = !b.expect && !ctx->force_legacy && b.params.min_diags >= 2 * (b.params.tb_diags + 1) + 2 &&
-             max_live_doubles + 4 * 6 * (int64_t)b.bw + 16 < 0x7ffffff0;
+    // E-step layout: 10 doubles per live cell, 11 where a total is evaluated (all forward and backward values)
+    b.cell_doubles = b.expect ? 10 : 1; b.total_extra = b.expect ? 1 : 5;
+    const int64_t live_need = b.expect ? (b.ring_cells + 2) * 11 : max_live_doubles;
+    b.fast = !ctx->force_legacy && b.params.min_diags >= 2 * (b.params.tb_diags + 1) + 2 &&
+             live_need + 4 * 11 * (int64_t)b.bw + 16 < (b.expect ? 0x08000000 : 0x7ffffff0);   // E-step: up to 1 GiB of ring per region
     int occ = 1;
     int64_t slot_bytes = 0;
     if (b.fast) {
@@ -334,14 +349,14 @@ int plan_memory(phmm_ctx *ctx) {
         b.wg = pow2_at_least(b.bw);
         b.wcap = ctx->opt_wcap ? ctx->opt_wcap : std::max<int32_t>(64, std::min<int32_t>(512, b.wg));
         // bump allocation with wrap-around wastes at most one diagonal's worth at the end of the ring
-        b.ring_doubles = max_live_doubles + 4 * 6 * (int64_t)b.bw + 16;
+        b.ring_doubles = live_need + 4 * 11 * (int64_t)b.bw + 16;
         b.dcap += 4;
         b.tcap = b.dcap / TOTAL_EVERY + 4;
         // one 16-byte record per diagonal of every region (k_records)
         b.rec_off.assign(nreg + 1, 0);
         for (int64_t i = 0; i < nreg; i++) b.rec_off[i + 1] = b.rec_off[i] + (int64_t)b.regions[i].lx + b.regions[i].ly + 1;
         b.fb2_smem = (size_t)2 * CS * b.wcap * 8 + FB2_TAB * 8 + 2 * FB2_RQ * sizeof(DiagRec);
-        occ = fb2_occupancy(b.nw, sw, b.fb2_smem);
+        occ = fb2_occupancy(b.nw, sw, b.expect, b.fb2_smem);
         if (occ < 1) return fail(ctx, PHMM_E_CUDA, "k_fb2 does not fit on this device");
         slot_bytes = b.ring_doubles * 8 + (int64_t)4 * NS * b.wg * 8 +
                      (int64_t)2 * CS * b.wcap * 8 + ((int64_t)b.tcap + b.wg) * 8;
@@ -416,7 +431,7 @@ int plan_memory(phmm_ctx *ctx) {
         k_records<<<(unsigned)((nreg + 63) / 64), 64, 0, ctx->stream>>>(
             ctx->d_regions.as<Region>(), ctx->d_runs.as<Run>(), (int)nreg, b.dp, ctx->d_tboff.as<int64_t>(), ctx->d_tbp.as<int32_t>(),
             reinterpret_cast<const int32_t *>(ctx->d_geom.as<char>() + offsetof(RegionGeom, tracebacks)), (int)(sizeof(RegionGeom) / 4),
-            b.ring_doubles, b.wcap, ctx->d_recoff.as<int64_t>(), ctx->d_recs.as<DiagRec>());
+            b.ring_doubles, b.wcap, b.cell_doubles, b.total_extra, ctx->d_recoff.as<int64_t>(), ctx->d_recs.as<DiagRec>());
         CK(cudaGetLastError());
     }
     return PHMM_OK;
@@ -542,7 +557,8 @@ int do_run(phmm_ctx *ctx) {
         f2.wcap = b.wcap;
         f2.dbg = ctx->opt_dbg;
         f2.px = fa.px; f2.py = fa.py; f2.pw = fa.pw; f2.npairs = fa.npairs;
-        fb2_launch(b.nw, ctx->model.has_switch != 0, f2, b.fb_slots, b.fb2_smem, ctx->stream);
+        f2.expT = fa.expT; f2.expE = fa.expE; f2.expLL = fa.expLL;
+        fb2_launch(b.nw, ctx->model.has_switch != 0, b.expect, f2, b.fb_slots, b.fb2_smem, ctx->stream);
         CK(cudaGetLastError());
     } else {
         rc = b.nw == 1 ? launch_fwdbwd<1>(ctx, fa, b.fb_slots, b.expect)

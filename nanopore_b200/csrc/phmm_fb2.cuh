@@ -70,6 +70,9 @@ struct Fb2Args {
     // outputs
     int32_t *px, *py, *pw;
     int32_t *npairs;
+    unsigned long long *expT;    // EXPECT: per region 25 transition counts (2^-32 fixed point)
+    unsigned long long *expE;    // EXPECT: per region 80 emission counts
+    double *expLL;               // EXPECT: per region summed total log-probability
     int32_t dbg;                 // timing experiments only (results are wrong when non-zero)
 };
 
@@ -232,7 +235,7 @@ __device__ __forceinline__ double fold_seq(int n, const char *ctab, F f) {
 // ---------------------------------------------------------------------------
 __global__ void k_records(const Region *regions, const Run *runs, int n_regions, DevParams p, const int64_t *tb_off,
                           const int32_t *tbp, const int32_t *ntb, int ntb_stride, int64_t ring_doubles, int wcap,
-                          const int64_t *rec_off, DiagRec *recs) {
+                          int cell_doubles, int total_extra, const int64_t *rec_off, DiagRec *recs) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_regions) return;
     const Region reg = regions[r];
@@ -244,7 +247,9 @@ __global__ void k_records(const Region *regions, const Run *runs, int n_regions,
     DiagRec *out = recs + rec_off[r];
     BandIter it;
     it.init(runs + reg.run0, reg.nrun, reg.lx, reg.ly, p.expansion);
-    int roff = 0, rsz = 0, tk = 0;
+    // diagonal 0 (the single cell (0,0)) gets a slot too: the E-step reads its forward values back
+    int roff = 0, rsz = cell_doubles, tk = 0;
+    { DiagRec r0; r0.off = 0; r0.xlo = 0; r0.w = 1; r0.pad = 0; out[0] = r0; }
     int P = tb[0];
     int TF = P - (P == nd ? 0 : tbd);
     int Pn = ntbr > 1 ? tb[1] : nd;
@@ -257,7 +262,7 @@ __global__ void k_records(const Region *regions, const Run *runs, int n_regions,
         it.diag(d, xlo, w);
         const int tf = d <= TF ? TF : TFn;
         const bool tot = (tf - d) % TOTAL_EVERY == 0;
-        const int es = w * (tot ? 6 : 1);
+        const int es = w * (cell_doubles + (tot ? total_extra : 0));
         int off = roff + rsz;
         if ((int64_t)off + es > ring_doubles) off = 0;
         roff = off; rsz = es;
@@ -289,7 +294,9 @@ __device__ __forceinline__ DiagRec ld_rec(const DiagRec *p) {
 #ifndef PHMM_MB4
 #define PHMM_MB4 5
 #endif
-constexpr int fb2_min_blocks(int nw) { return nw == 8 ? 2 : (nw == 4 ? PHMM_MB4 : 8); }
+constexpr int fb2_min_blocks(int nw, bool expect) {
+    return expect ? (nw == 8 ? 1 : (nw == 4 ? 3 : 6)) : (nw == 8 ? 2 : (nw == 4 ? PHMM_MB4 : 8));
+}
 
 // Shared-memory diagonal buffers.  Cell (d, x) lives in column (x - (d >> 1)) & (wcap - 1) of the buffer of parity
 // d & 1, so a cell overwrites its own `middle` predecessor (d-2, x-1) and its `lower` / `upper` predecessors sit in
@@ -298,8 +305,13 @@ constexpr int fb2_min_blocks(int nw) { return nw == 8 ? 2 : (nw == 4 ? PHMM_MB4 
 // neighbours without any in-band test, whatever the band does at its ends, as long as the columns of three
 // consecutive diagonals (plus one either side) do not alias modulo wcap (REC_FAST3, decided by k_records).
 // Other diagonals take the guarded path and then restore the invariant by clearing every out-of-band column.
-template <int NW, bool SWITCH>
-__global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW)) k_fb2(const __grid_constant__ Fb2Args a) {
+// EXPECT (Baum-Welch E-step, replaces `cactus_realign --outputExpectations`): the ring keeps all five forward AND
+// backward values of every cell of the live window (10 doubles per cell, 11 where a total is evaluated), the
+// posterior phase is replaced by an expectation phase over the same diagonals -- every cell independent, no barriers
+// -- that evaluates the 15 transitions of SURVEY.md A.8 with the window's totals and accumulates 2^-32 fixed-point
+// counts (transitions in per-thread registers, emissions in shared memory).
+template <int NW, bool SWITCH, bool EXPECT>
+__global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(const __grid_constant__ Fb2Args a) {
     constexpr int NC = NW * 32;            // threads; all compute
     constexpr int NTA = NC;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -311,6 +323,14 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW)) k_fb2(const __gri
     DiagRec *const srec = reinterpret_cast<DiagRec *>(sct + FB2_TAB);            // [2][FB2_RQ]
     __shared__ int s_region;
     __shared__ int s_npairs;
+    __shared__ EmisTables etab;                        // EXPECT
+    __shared__ unsigned long long sT[EXPECT ? 25 : 1];
+    __shared__ unsigned long long sE[EXPECT ? 80 : 1];
+    constexpr int DOT = EXPECT ? 10 : 5;               // block of the per-cell dot products within a diagonal's ring entry
+    if (EXPECT) {
+        for (int i = tid; i < 25; i += NC) etab.eM[i] = a.m.eM[i];
+        if (tid < 5) { etab.eX[tid] = a.m.eX[tid]; etab.eY[tid] = a.m.eY[tid]; }
+    }
 
     if (tid == 0) {
         sct[0] = -0.009350833524763; sct[1] = 0.130659527668286; sct[2] = 0.498799810682272; sct[3] = 0.693203116424741;
@@ -370,6 +390,14 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW)) k_fb2(const __gri
         const uint8_t *Y = a.reads + reg.yoff;
         const int lx = reg.lx, ly = reg.ly, nd = lx + ly;
         if (tid == 0) s_npairs = 0;
+        unsigned long long accT[EXPECT ? EXP_NT : 1];               // this thread's transition counts of the region
+        double ll = 0.0;                                            // thread 0
+        if (EXPECT) {
+#pragma unroll
+            for (int k = 0; k < EXP_NT; k++) accT[k] = 0ull;
+            for (int i = tid; i < 25; i += NC) sT[i] = 0ull;
+            for (int i = tid; i < 80; i += NC) sE[i] = 0ull;
+        }
         if (nd > 0) {
             const int32_t *tb = a.tbp + a.tb_off[ridx];
             const int ntb = a.ntb[(int64_t)ridx * a.ntb_stride];
@@ -388,6 +416,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW)) k_fb2(const __gri
                 if (reg.ragged_left) v = (tid == S_LX || tid == S_LY) ? 0.0 : PHMM_NEG_INF;
                 else v = (tid == S_M) ? 0.0 : PHMM_NEG_INF;
                 sbuf[tid] = v;
+                if (EXPECT) ring[tid] = v;                            // diagonal 0: slot 0 of the ring, width 1
             }
             int xlo1 = 0, w1 = 1, f1 = 0;                             // diagonal d-1
             int xlo2 = 0, w2 = 0, f2 = 0;                             // diagonal d-2 (w2 = 0: absent)
@@ -429,7 +458,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW)) k_fb2(const __gri
                             st_col<true>(p0, o);
                             if (!(a.dbg & 2)) {
                             rg[i] = o[S_M];
-                            if (tot) {
+                            if (tot || EXPECT) {
 #pragma unroll
                                 for (int s = 1; s < NS; s++) rg[s * w + i] = o[s];
                             }
@@ -453,7 +482,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW)) k_fb2(const __gri
                             fwd_cell3<SWITCH, true>(tabs, pl, okl, pu, oku, pm, okm, cX, cY, o);
                             st_col<false>(p0, o);
                             rg[i] = o[S_M];
-                            if (tot) {
+                            if (tot || EXPECT) {
 #pragma unroll
                                 for (int s = 1; s < NS; s++) rg[s * w + i] = o[s];
                             }
@@ -532,15 +561,20 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW)) k_fb2(const __gri
                                         bwd_cell3<SWITCH, false>(tabs, pl, true, pu, true, p0, true, cXn, cYn, o);
                                         st_col<true>(p0, o);
                                         const double sM = fM + o[S_M];
-                                        // F_M is not needed again below traced_from; above it the next window sweeps the
-                                        // diagonal once more, and only the one next to the range feeds a total
-                                        if (dd <= traced_from) rg[i] = sM;
-                                        else if (dd == traced_from + 1) ovs[i] = sM;
+                                        if (EXPECT) {
+#pragma unroll
+                                            for (int s = 0; s < NS; s++) rg[(NS + s) * rb.w + i] = o[s];
+                                        } else {
+                                            // F_M is not needed again below traced_from; above it the next window sweeps the
+                                            // diagonal once more, and only the one next to the range feeds a total
+                                            if (dd <= traced_from) rg[i] = sM;
+                                            else if (dd == traced_from + 1) ovs[i] = sM;
+                                        }
                                         if (dots) {
                                             double t = sM;
 #pragma unroll
                                             for (int s = 1; s < NS; s++) t = logadd_t(t, rg[s * rb.w + i] + o[s], ctab);
-                                            rg[5 * rb.w + i] = t;
+                                            rg[DOT * rb.w + i] = t;
                                         }
                                     }
                                 } else {
@@ -566,13 +600,18 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW)) k_fb2(const __gri
                                         }
                                         st_col<false>(p0, o);
                                         const double sM = rg[i] + o[S_M];
-                                        if (dd <= traced_from) rg[i] = sM;
-                                        else if (dd == traced_from + 1) ovs[i] = sM;
+                                        if (EXPECT) {
+#pragma unroll
+                                            for (int s = 0; s < NS; s++) rg[(NS + s) * rb.w + i] = o[s];
+                                        } else {
+                                            if (dd <= traced_from) rg[i] = sM;
+                                            else if (dd == traced_from + 1) ovs[i] = sM;
+                                        }
                                         if (dots) {
                                             double t = sM;
 #pragma unroll
                                             for (int s = 1; s < NS; s++) t = logadd_t(t, rg[s * rb.w + i] + o[s], ctab);
-                                            rg[5 * rb.w + i] = t;
+                                            rg[DOT * rb.w + i] = t;
                                         }
                                     }
                                 }
@@ -596,19 +635,44 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW)) k_fb2(const __gri
                     for (int k = tid; k < ((a.dbg & 64) ? 0 : nk); k += NTA) {
                         const int dd = traced_from - TOTAL_EVERY * k;
                         const DiagRec r0 = rec[dd];
-                        const double *cd = ring + r0.off + 5 * r0.w;
+                        const double *cd = ring + r0.off + DOT * r0.w;
                         double total = fold_seq(r0.w, ctab, [&](int i) { return cd[i]; });
                         if (dd < d) {
                             const DiagRec r1 = rec[dd + 1];
                             const double *sm = dd + 1 > traced_from ? ovs : ring + r1.off;
-                            const double t1 = fold_seq(r1.w, ctab, [&](int i) { return sm[i]; });
+                            const double *fm1 = ring + r1.off, *bm1 = fm1 + NS * r1.w;                     // EXPECT: F_M and B_M apart
+                            const double t1 = EXPECT ? fold_seq(r1.w, ctab, [&](int i) { return fm1[i] + bm1[i]; })
+                                                     : fold_seq(r1.w, ctab, [&](int i) { return sm[i]; });
                             total = logadd_t(total, t1, ctab);
                         }
                         totals[k] = total;
                     }
                     __syncthreads();
+                    if (EXPECT) {
+                        // phase 3E: expectations, one warp per diagonal, cells independent; log-likelihood = the totals of the
+                        // posterior diagonals added in descending order (the scalar order)
+                        if (tid == 0)
+                            for (int dd = traced_from; dd > traced_to; dd--) ll += totals[(traced_from - dd) / TOTAL_EVERY];
+                        for (int dd = traced_from - (tid >> 5); dd > traced_to; dd -= NW) {
+                            const DiagRec r0 = rec[dd], r1 = rec[dd - 1];
+                            DiagRec r2 = r1;
+                            int w2e = 0;
+                            if (dd - 2 >= traced_to) { r2 = rec[dd - 2]; w2e = r2.w; }     // older forward diagonals are gone in the scalar schedule
+                            const double total = totals[(traced_from - dd) / TOTAL_EVERY];
+                            const double *bd = ring + r0.off + NS * r0.w;
+                            for (int i = tid & 31; i < r0.w; i += 32) {
+                                const int x = r0.xlo + i, y = dd - x;
+                                const int cX = x >= 1 ? X[x - 1] : 4;
+                                const int cY = y >= 1 ? Y[y - 1] : 4;
+                                double B[NS];
+#pragma unroll
+                                for (int s = 0; s < NS; s++) B[s] = bd[s * r0.w + i];
+                                expect_cell<SWITCH>(a.m, etab, ring + r1.off, r1.xlo, r1.w, ring + r2.off, r2.xlo, w2e, x, cX, cY, B, total, accT, sE);
+                            }
+                        }
+                    }
                     // phase 3: posterior match probabilities, one warp per diagonal
-                    for (int dd = traced_from - (tid >> 5); dd > ((a.dbg & 128) ? traced_from : traced_to); dd -= NW) {
+                    for (int dd = EXPECT ? traced_to : traced_from - (tid >> 5); dd > ((a.dbg & 128) ? traced_from : traced_to); dd -= NW) {
                         const DiagRec r0 = rec[dd];
                         const double total = totals[(traced_from - dd) / TOTAL_EVERY];
                         const double *sm = ring + r0.off;
@@ -653,8 +717,20 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW)) k_fb2(const __gri
                 xlo1 = xlo; w1 = w; f1 = rc.pad;
             }
         }
+        if (EXPECT) {
+#pragma unroll
+            for (int k = 0; k < EXP_NT; k++)
+                if (accT[k]) atomicAdd(&sT[EXP_SLOT_TR[k]], accT[k]);
+        }
         __syncthreads();
-        if (tid == 0) a.npairs[ridx] = s_npairs;
+        if (tid == 0) {
+            a.npairs[ridx] = s_npairs;
+            if (EXPECT) a.expLL[ridx] = ll;
+        }
+        if (EXPECT) {
+            for (int i = tid; i < 25; i += NC) a.expT[(int64_t)ridx * 25 + i] = sT[i];
+            for (int i = tid; i < 80; i += NC) a.expE[(int64_t)ridx * 80 + i] = sE[i];
+        }
     }
 }
 

@@ -129,9 +129,12 @@ def test_mixed_lengths_and_degenerate_reads():
     ctx.close()
 
 
-def test_expectations_match_oracle(trained):
+@pytest.mark.parametrize("legacy", [0, 1])
+def test_expectations_match_oracle(trained, legacy):
+    """E-step on the windowed kernel (k_fb2<EXPECT>) and on the first-generation kernel (k_fwdbwd<EXPECT>)."""
     t, e = trained
     ctx = capi.PhmmContext(0, t, e, 1)
+    ctx.set_option("legacy_kernel", legacy)
     model = oracle.Model(t, e)
     b = synth.make_batch(5, 800, 2400, seed=11)
     ctx.set_reference(b.ref)
