@@ -291,7 +291,7 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         cells_rank = float(st["cells"])
-        achieved = BYTES_PER_CELL * cells_rank / (fb_ms / args.steps * 1e-3) / 1e9      # GB/s of the k_fwdbwd launch (per GPU)
+        achieved = BYTES_PER_CELL * cells_rank / (fb_ms / args.steps * 1e-3) / 1e9      # algorithmic GB/s of the k_fb2 launch (per GPU)
         line = {"metric": METRIC, "value": reads_total * args.steps / (ms * 1e-3), "unit": "reads/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
