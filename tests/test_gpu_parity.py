@@ -265,6 +265,18 @@ def test_kernel_variants_agree_with_the_oracle(opts):
     ctx.close()
 
 
+def test_pair_buffers_grow_when_a_low_threshold_overflows_them():
+    """threshold 1e-6 keeps most band cells as pairs: far more than the first capacity guess (8 per row), so the
+    library re-runs with larger buffers (x4 per attempt) and must still return the oracle's pairs and CIGARs."""
+    ctx = capi.PhmmContext(0)
+    b = synth.make_batch(3, 500, 1500, seed=91, global_form=False)
+    ctx.set_reference(b.ref)
+    ops, off, post = gpu_vs_oracle(ctx, oracle.Model(), b, 50, threshold=1e-6)
+    per_row = (post["off"][1:] - post["off"][:-1]) / np.array([len(b.read(i)) for i in range(b.n)])
+    assert per_row.max() > 10                                   # the first guess (8 per row + 1024) was exceeded
+    ctx.close()
+
+
 def test_option_errors():
     ctx = capi.PhmmContext(0)
     with pytest.raises(capi.PhmmError):
