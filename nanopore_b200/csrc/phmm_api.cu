@@ -79,7 +79,7 @@ struct phmm_ctx {
     std::string err;
     DevModel model;
     int64_t mem_budget = 0;
-    bool force_legacy = false;
+    bool force_legacy = false, decode_full_sweep = false;
     int opt_warps = 0, opt_wcap = 0, opt_dbg = 0;             // tests: run the first-generation kernel (k_fwdbwd) instead of k_fb2
     DevBuf d_ref; int64_t ref_len = -1;
     DevBuf d_reads, d_regions, d_runs, d_geom, d_order, d_counter;
@@ -370,7 +370,7 @@ int plan_memory(phmm_ctx *ctx) {
     const int64_t fixed = b.total_pair_cap * 12 + b.total_mrun_cap * 12 + nreg * (sizeof(Region) + sizeof(RegionGeom) + 64) +
                           (b.fast ? b.rec_off[nreg] * (int64_t)sizeof(DiagRec) + nreg * 8 : 0);
     const int64_t dec_slot_bytes = (int64_t)(b.max_lx + 1) * 4 + (int64_t)(b.max_ly + 1) * 4 + (int64_t)(b.max_nd + 4) * 8 +
-                                   (int64_t)(b.max_pairs + 1) * 16 + (int64_t)2 * (b.max_lx + 2) * 8 + (int64_t)3 * b.bw * 12;
+                                   (int64_t)(b.max_pairs + 1) * 16 + (int64_t)2 * (b.max_lx + 2) * 8 + (int64_t)4 * b.bw * 12;
     int64_t avail = budget(ctx) - fixed;
     if (avail < slot_bytes + dec_slot_bytes) return fail(ctx, PHMM_E_NOMEM, "memory budget too small for one region of this batch");
     // measured (profiles/r01b_phase_breakdown.txt, tune15): 2-warp decode blocks, 16 per SM, beat 4 warps x 8
@@ -415,8 +415,8 @@ int plan_memory(phmm_ctx *ctx) {
         CK(ctx->d_wre.ensure((size_t)dec_want * (b.max_pairs + 1) * 8));
         CK(ctx->d_pred.ensure((size_t)dec_want * (b.max_pairs + 1) * 4));
         CK(ctx->d_colmap.ensure((size_t)dec_want * 2 * (b.max_lx + 2) * 8));
-        CK(ctx->d_sring.ensure((size_t)dec_want * 3 * b.bw * 8));
-        CK(ctx->d_lring.ensure((size_t)dec_want * 3 * b.bw * 4));
+        CK(ctx->d_sring.ensure((size_t)dec_want * 4 * b.bw * 8));
+        CK(ctx->d_lring.ensure((size_t)dec_want * 4 * b.bw * 4));
         CK(ctx->d_mrx.ensure((size_t)b.total_mrun_cap * 4 + 16));
         CK(ctx->d_mry.ensure((size_t)b.total_mrun_cap * 4 + 16));
         CK(ctx->d_mrn.ensure((size_t)b.total_mrun_cap * 4 + 16));
@@ -582,6 +582,9 @@ int do_run(phmm_ctx *ctx) {
         da.sring = ctx->d_sring.as<int64_t>(); da.lring = ctx->d_lring.as<int32_t>(); da.bw = b.bw;
         da.mrx = ctx->d_mrx.as<int32_t>(); da.mry = ctx->d_mry.as<int32_t>(); da.mrn = ctx->d_mrn.as<int32_t>();
         da.nmruns = ctx->d_nmruns.as<int32_t>(); da.score = ctx->d_score.as<int64_t>();
+        da.regular = reinterpret_cast<const int32_t *>(ctx->d_geom.as<char>() + offsetof(RegionGeom, regular));
+        da.regular_stride = ctx->decode_full_sweep ? 0 : (int32_t)(sizeof(RegionGeom) / 4);
+        if (ctx->decode_full_sweep) da.regular = ctx->d_counter.as<int32_t>() + 4;      // a zero: no region takes the shortcut
         if (b.nw == 1) k_decode<1><<<b.dec_slots, 32, 0, ctx->stream>>>(da);
         else k_decode<2><<<b.dec_slots, 64, 0, ctx->stream>>>(da);
         CK(cudaGetLastError());
@@ -711,6 +714,7 @@ int phmm_set_option(phmm_ctx *ctx, const char *name, int64_t value) {
     if (!ctx || !name) return PHMM_E_ARG;
     const std::string n(name);
     if (n == "legacy_kernel") ctx->force_legacy = value != 0;
+    else if (n == "decode_full_sweep") ctx->decode_full_sweep = value != 0;
     else if (n == "warps") {
         if (value != 0 && value != 2 && value != 4 && value != 8) return fail(ctx, PHMM_E_ARG, "warps must be 0, 2, 4 or 8");
         ctx->opt_warps = (int)value;

@@ -39,6 +39,9 @@ struct RegionGeom {                   // written by the geometry kernel
     int32_t tracebacks;
     int32_t diagonals;
     int64_t max_live_doubles;         // peak of the windowed kernel's ring (1 or 6 doubles per cell, see phmm_fb2.cuh)
+    int32_t regular;                  // 1: both band edges move right by 0 or 1 cell per diagonal, so every band cell has a
+                                      //    predecessor and a successor in the band (reachable from (0,0), reaches (lx,ly))
+    int32_t pad;
 };
 
 struct DevModel {                     // log-space stateMachine5

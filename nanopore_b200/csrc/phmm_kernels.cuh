@@ -66,9 +66,13 @@ __global__ void k_geometry(const Region *regions, const Run *runs, int n_regions
     int traced_to = 0;
     int32_t *tb = tbp + tb_off[r];
     const int tb_cap = (int)(tb_off[r + 1] - tb_off[r]);
+    int plo = 0, phi = 0, regular = 1;                  // band edges of the previous diagonal (diagonal 0: x = 0)
     for (int d = 1; d <= nd; d++) {
         int xlo, w;
         it.diag(d, xlo, w);
+        const int xhi = xlo + w - 1;
+        if (xlo < plo || xlo > plo + 1 || xhi < phi || xhi > phi + 1 || w < 1) regular = 0;
+        plo = xlo; phi = xhi;
         wbuf[d & 255] = w;
         g.cells += w;
         live += w; live_d++;
@@ -90,6 +94,7 @@ __global__ void k_geometry(const Region *regions, const Run *runs, int n_regions
     }
     g.max_live_cells = max_live;
     g.max_live_diags = max_live_d;
+    g.regular = regular; g.pad = 0;
     // second sweep: ring usage of the windowed kernel (1 double per cell, 6 on total-probability diagonals)
     g.max_live_doubles = 0;
     if (nd > 0 && g.tracebacks <= tb_cap) {
@@ -558,7 +563,8 @@ struct DecArgs {
     int32_t *dstart; int32_t *dfill; int32_t max_nd;          // pairs bucketed by anti-diagonal
     int32_t *sidx; int64_t *wre; int32_t *pred; int32_t max_pairs;
     int64_t *colmap;                                          // 2 * max_lx: (diagonal << 32 | sorted position) by column
-    int64_t *sring; int32_t *lring; int32_t bw;               // 3 * bw each
+    int64_t *sring; int32_t *lring; int32_t bw;               // 4 * bw each: three diagonals + a snapshot for skips
+    const int32_t *regular; int32_t regular_stride;           // RegionGeom::regular, strided (int32 units)
     // outputs
     int32_t *mrx, *mry, *mrn;                                 // match runs in reverse order (region-local sequence coords)
     int32_t *nmruns;                                          // per region
@@ -571,6 +577,7 @@ __global__ void __launch_bounds__(NW * 32) k_decode(const __grid_constant__ DecA
     const int tid = threadIdx.x;
     __shared__ int s_region;
     __shared__ int s_part[NT];
+    __shared__ int s_dn;                              // next anti-diagonal that holds a pair (skip search)
     const int slot = blockIdx.x;
     int32_t *const sumx = a.sumx + (int64_t)slot * (a.max_lx + 1);
     int32_t *const sumy = a.sumy + (int64_t)slot * (a.max_ly + 1);
@@ -580,8 +587,8 @@ __global__ void __launch_bounds__(NW * 32) k_decode(const __grid_constant__ DecA
     int64_t *const wre = a.wre + (int64_t)slot * (a.max_pairs + 1);
     int32_t *const pred = a.pred + (int64_t)slot * (a.max_pairs + 1);
     int64_t *const colmap = a.colmap + (int64_t)slot * 2 * (a.max_lx + 2);
-    int64_t *const sr = a.sring + (int64_t)slot * 3 * a.bw;
-    int32_t *const lr = a.lring + (int64_t)slot * 3 * a.bw;
+    int64_t *const sr = a.sring + (int64_t)slot * 4 * a.bw;
+    int32_t *const lr = a.lring + (int64_t)slot * 4 * a.bw;
 
     for (;;) {
         block_sync<NW>();
@@ -642,7 +649,20 @@ __global__ void __launch_bounds__(NW * 32) k_decode(const __grid_constant__ DecA
             sidx[pos] = i;
         }
         block_sync<NW>();
-        // 5. wavefront over the band
+        // 5. wavefront over the band.
+        //    Skipping pairless stretches.  In a regular band (RegionGeom::regular: both edges move right by 0 or 1 per
+        //    diagonal) cell (d1, x') reaches cell (d2, x) through band cells iff x' <= x <= x' + (d2 - d1), and without
+        //    pairs in between scores only propagate, `lower` (the smaller x) preferred on ties: cell (d2, x) ends up
+        //    with the LEFTMOST maximum of diagonal d1 over x' in [x - (d2 - d1), x].  So after a run of pairless
+        //    diagonals the block looks for the next diagonal dn that holds a pair, fills dn-2 and dn-1 from the current
+        //    diagonal with that window maximum, walks the band iterator there, and resumes at dn; if no pair is left
+        //    the final cell is evaluated the same way.  The chained-global alignments of this path spend most of their
+        //    diagonals in pairless leading / trailing deletions.
+        const bool regular = a.regular[(int64_t)ridx * a.regular_stride] != 0;
+        constexpr int SKIP_AFTER = 8, SKIP_MIN = 64;
+        int empty_run = 0;
+        bool finished = false;
+        int64_t fin_s = 0; int fin_k = -1;                // thread 0: result when the sweep ends by a skip
         BandIter it;
         it.init(a.runs + reg.run0, reg.nrun, lx, ly, a.p.expansion);
         if (tid == 0) { sr[0] = 0; lr[0] = -1; }
@@ -657,8 +677,11 @@ __global__ void __launch_bounds__(NW * 32) k_decode(const __grid_constant__ DecA
             int xlo, w;
             it.diag(d, xlo, w);
             // stage pairs of diagonal d+1
+            int pairs_next = 0;
             if (d + 1 <= nd) {
-                for (int k = dstart[d + 1] + tid; k < dstart[d + 2]; k += NT) {
+                const int k0 = dstart[d + 1], k1 = dstart[d + 2];
+                pairs_next = k1 - k0;
+                for (int k = k0 + tid; k < k1; k += NT) {
                     const int pi = sidx[k];
                     colmap[((d + 1) & 1) * (lx + 2) + px[pi] + 1] = ((int64_t)(d + 1) << 32) | (uint32_t)k;
                 }
@@ -693,11 +716,78 @@ __global__ void __launch_bounds__(NW * 32) k_decode(const __grid_constant__ DecA
             }
             xlo2 = xlo1; w2 = w1; xlo1 = xlo; w1 = w;
             block_sync<NW>();
+            // ---- skip a pairless stretch (all conditions are uniform over the block) ----
+            empty_run = pairs_next == 0 ? empty_run + 1 : 0;
+            if (regular && empty_run >= SKIP_AFTER && d + SKIP_MIN < nd) {
+                // next diagonal > d+1 that holds a pair
+                int dn = nd + 1;
+                for (int base = d + 2; base <= nd; base += NT) {
+                    if (tid == 0) s_dn = 0x7fffffff;
+                    block_sync<NW>();
+                    const int dd = base + tid;
+                    if (dd <= nd && dstart[dd + 1] > dstart[dd]) atomicMin(&s_dn, dd);
+                    block_sync<NW>();
+                    const int f = s_dn;
+                    block_sync<NW>();
+                    if (f != 0x7fffffff) { dn = f; break; }
+                }
+                if (dn > nd || dn - d >= SKIP_MIN) {
+                    // snapshot of the current diagonal d (band xlo1, w1 after the shift above)
+                    const int xs = xlo1, ws = w1, xse = xlo1 + w1 - 1;
+                    int64_t *const sS = sr + (int64_t)3 * a.bw;
+                    int32_t *const sL = lr + (int64_t)3 * a.bw;
+                    {
+                        const int64_t *Sd = sr + (int64_t)(d % 3) * a.bw;
+                        const int32_t *Ld = lr + (int64_t)(d % 3) * a.bw;
+                        for (int i = tid; i < ws; i += NT) { sS[i] = Sd[i]; sL[i] = Ld[i]; }
+                    }
+                    block_sync<NW>();
+                    if (dn > nd) {
+                        // no pair left: the final cell (nd, lx) takes the leftmost maximum of its window on diagonal d
+                        if (tid == 0) {
+                            const int delta = nd - d;
+                            const int ja = max(xs, lx - delta), jb = min(xse, lx);
+                            int64_t best = -1; int bl = -1;
+                            for (int j = ja; j <= jb; j++) { const int64_t v = sS[j - xs]; if (v > best) { best = v; bl = sL[j - xs]; } }
+                            fin_s = best; fin_k = bl;
+                        }
+                        finished = true;
+                        break;
+                    }
+                    // walk the band to dn-1, keeping the extents of dn-2 and dn-1
+                    for (int dd = d + 1; dd <= dn - 1; dd++) {
+                        int xa, wa;
+                        it.diag(dd, xa, wa);
+                        xlo2 = xlo1; w2 = w1; xlo1 = xa; w1 = wa;
+                    }
+                    for (int t = dn - 2; t <= dn - 1; t++) {
+                        const int xt = t == dn - 2 ? xlo2 : xlo1, wt = t == dn - 2 ? w2 : w1, delta = t - d;
+                        int64_t *St = sr + (int64_t)(t % 3) * a.bw;
+                        int32_t *Lt = lr + (int64_t)(t % 3) * a.bw;
+                        for (int i = tid; i < wt; i += NT) {
+                            const int x = xt + i;
+                            const int ja = max(xs, x - delta), jb = min(xse, x);
+                            int64_t best = -1; int bl = -1;
+                            for (int j = ja; j <= jb; j++) { const int64_t v = sS[j - xs]; if (v > best) { best = v; bl = sL[j - xs]; } }
+                            St[i] = best; Lt[i] = bl;
+                        }
+                    }
+                    // pairs of diagonal dn into the column map, as the sweep would have done at dn-1
+                    for (int k = dstart[dn] + tid; k < dstart[dn + 1]; k += NT) {
+                        const int pi = sidx[k];
+                        colmap[(dn & 1) * (lx + 2) + px[pi] + 1] = ((int64_t)dn << 32) | (uint32_t)k;
+                    }
+                    block_sync<NW>();
+                    d = dn - 1;                         // the loop continues with diagonal dn
+                    empty_run = 0;
+                }
+                else empty_run = 0;                     // a pair is near: sweep on, search again after the next pairless run
+            }
         }
         // 6. traceback into match runs (reverse order), thread 0
         if (tid == 0) {
-            const int64_t fs = sr[(int64_t)(nd % 3) * a.bw];
-            int k = lr[(int64_t)(nd % 3) * a.bw];
+            const int64_t fs = finished ? fin_s : sr[(int64_t)(nd % 3) * a.bw];
+            int k = finished ? fin_k : lr[(int64_t)(nd % 3) * a.bw];
             int nr = 0;
             int rx = -2, ry = -2, rn = 0;             // current run: starts at (rx,ry), length rn
             while (k >= 0) {
