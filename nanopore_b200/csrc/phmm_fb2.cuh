@@ -295,7 +295,7 @@ __device__ __forceinline__ DiagRec ld_rec(const DiagRec *p) {
 #define PHMM_MB4 5
 #endif
 constexpr int fb2_min_blocks(int nw, bool expect) {
-    return expect ? (nw == 8 ? 1 : (nw == 4 ? 3 : 6)) : (nw == 8 ? 2 : (nw == 4 ? PHMM_MB4 : 8));
+    return expect ? (nw == 8 ? 2 : (nw == 4 ? 4 : 8)) : (nw == 8 ? 2 : (nw == 4 ? PHMM_MB4 : 8));
 }
 
 // Shared-memory diagonal buffers.  Cell (d, x) lives in column (x - (d >> 1)) & (wcap - 1) of the buffer of parity
@@ -390,11 +390,8 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
         const uint8_t *Y = a.reads + reg.yoff;
         const int lx = reg.lx, ly = reg.ly, nd = lx + ly;
         if (tid == 0) s_npairs = 0;
-        unsigned long long accT[EXPECT ? EXP_NT : 1];               // this thread's transition counts of the region
         double ll = 0.0;                                            // thread 0
         if (EXPECT) {
-#pragma unroll
-            for (int k = 0; k < EXP_NT; k++) accT[k] = 0ull;
             for (int i = tid; i < 25; i += NC) sT[i] = 0ull;
             for (int i = tid; i < 80; i += NC) sE[i] = 0ull;
         }
@@ -653,6 +650,9 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                         // posterior diagonals added in descending order (the scalar order)
                         if (tid == 0)
                             for (int dd = traced_from; dd > traced_to; dd--) ll += totals[(traced_from - dd) / TOTAL_EVERY];
+                        unsigned long long accT[EXP_NT];                // this thread's transition counts of the window:
+#pragma unroll
+                        for (int k = 0; k < EXP_NT; k++) accT[k] = 0ull; // registers only while this phase runs
                         for (int dd = traced_from - (tid >> 5); dd > traced_to; dd -= NW) {
                             const DiagRec r0 = rec[dd], r1 = rec[dd - 1];
                             DiagRec r2 = r1;
@@ -670,6 +670,9 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                                 expect_cell<SWITCH>(a.m, etab, ring + r1.off, r1.xlo, r1.w, ring + r2.off, r2.xlo, w2e, x, cX, cY, B, total, accT, sE);
                             }
                         }
+#pragma unroll
+                        for (int k = 0; k < EXP_NT; k++)
+                            if (accT[k]) atomicAdd(&sT[EXP_SLOT_TR[k]], accT[k]);
                     }
                     // phase 3: posterior match probabilities, one warp per diagonal
                     for (int dd = EXPECT ? traced_to : traced_from - (tid >> 5); dd > ((a.dbg & 128) ? traced_from : traced_to); dd -= NW) {
@@ -716,11 +719,6 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                 xlo2 = xlo1; w2 = w1; f2 = f1;
                 xlo1 = xlo; w1 = w; f1 = rc.pad;
             }
-        }
-        if (EXPECT) {
-#pragma unroll
-            for (int k = 0; k < EXP_NT; k++)
-                if (accT[k]) atomicAdd(&sT[EXP_SLOT_TR[k]], accT[k]);
         }
         __syncthreads();
         if (tid == 0) {

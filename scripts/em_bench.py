@@ -20,6 +20,8 @@ b = synth.make_batch(n, 8000, 50000, seed=4)
 p = em.parseRealignOptions("--diagonalExpansion=10 --splitMatrixBiggerThanThis=300")
 hmm = em._stock_start("fiveStateAsymmetric")
 r = Realigner(0)
+if os.environ.get("EM_WARPS"):
+    r.ctx.set_option("warps", int(os.environ["EM_WARPS"]))
 r.set_reference(b.ref)
 r.set_hmm(hmm)
 r.expectations(b, p)                                        # warm-up (allocations)
