@@ -176,8 +176,8 @@ int phmm_set_memory_budget(phmm_ctx *ctx, int64_t bytes);
 /* Tuning / test switches of the library itself (no counterpart in the reference).  Names:
  *   "legacy_kernel" 1: run the first-generation kernel (forward window wholly in HBM) instead of the
  *                      windowed shared-memory kernel; results are identical
- *   "decode_full_sweep" 1: the decode kernel sweeps every diagonal of the band instead of only those between the
- *                      first and the last diagonal that hold a posterior pair; results are identical
+ *   "decode_full_sweep" 1: the decode kernel sweeps every diagonal of the band instead of skipping stretches of
+ *                      diagonals that hold no posterior pair; results are identical
  *   "warps"         0 = choose by band width, else 2, 4 or 8 warps per DP region
  *   "smem_columns"  0 = choose, else the shared-memory diagonal buffer (power of two, 64..1024)
  *   "timing_experiment" bit mask that SKIPS parts of the windowed kernel to time the rest (1 forward sequence
