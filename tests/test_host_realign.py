@@ -184,3 +184,18 @@ def test_realign_cigar_target_fn_single_read(tmp_path, oracle_engine):
     assert len(pAs) == 1                                                   # utils.py:588-589
     r = oracle.realign(oracle.Model(), b.ref, b.read(0), b.ops(0), oracle.make_params(expansion=10))
     assert [(o.type, o.length) for o in pAs[0].operationList] == synth.unpack_ops(r["ops"])
+
+
+def test_command_line_entry_point(tmp_path, oracle_engine):
+    """scripts/realign_sam.py: SAM in, realigned SAM out (single process; under torchrun rank 0 does the same)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("realign_sam", os.path.join(root, "scripts", "realign_sam.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ref_fa, fq, sam_path, truth = make_experiment(str(tmp_path), seed=13)
+    out = str(tmp_path / "realigned.sam")
+    assert mod.main([sam_path, fq, ref_fa, out, "--gapGamma", "0.4"]) == 0
+    chained = str(tmp_path / "chained.sam")
+    realign.chainSamFile(sam_path, chained, fq, ref_fa)
+    check_against_oracle(ref_fa, fq, out, chained, oracle.Model(), 0.4, 0.0)
