@@ -37,34 +37,36 @@ def trainedModelPath(trainedModelFile, workDir):
 
 
 class AbstractMapper(Target):
-    """Base class for mappers. Inherit this class to create a mapper."""
+    """A mapper plugin produces `outputSamFile` in run(); the two methods below post-process that file in place."""
 
     def __init__(self, readFastqFile, readType, referenceFastaFile, outputSamFile, emptyHmmFile=None):
-        Target.__init__(self)
-        self.readFastqFile = readFastqFile
+        super().__init__()
+        self.readFastqFile, self.readType = readFastqFile, readType
         self.referenceFastaFile = referenceFastaFile
         self.outputSamFile = outputSamFile
-        self.readType = readType
-        self.emptyHmmFile = emptyHmmFile
+        self.emptyHmmFile = emptyHmmFile            # where doEm writes the trained model (pipeline.py:121)
+
+    def _scratch_copy(self, directory):
+        scratch = os.path.join(directory, "temp.sam")
+        shutil.copyfile(self.outputSamFile, scratch)
+        return scratch
 
     def chainSamFile(self):
-        """Converts the sam file so that there is at most one global alignment of each read."""
-        tempSamFile = os.path.join(self.getLocalTempDir(), "temp.sam")
-        shutil.copyfile(self.outputSamFile, tempSamFile)
-        chainSamFile(tempSamFile, self.outputSamFile, self.readFastqFile, self.referenceFastaFile)
+        """Rewrites outputSamFile with at most one (global) alignment per read and reference."""
+        chainSamFile(self._scratch_copy(self.getLocalTempDir()), self.outputSamFile, self.readFastqFile,
+                     self.referenceFastaFile)
 
     def realignSamFile(self, gapGamma=0.5, matchGamma=0.0, doEm=False, useTrainedModel=False,
                        trainedModelFile="blasr_hmm_0.txt"):
-        """Chains and then realigns the resulting global alignments."""
-        tempSamFile = os.path.join(self.getGlobalTempDir(), "temp.sam")
-        if useTrainedModel and doEm:
+        """Schedules chain -> [EM] -> realign of outputSamFile (same defaults and model choice as the reference:
+        doEm trains into emptyHmmFile, useTrainedModel loads a shipped / derived model, neither = stock model)."""
+        if doEm and useTrainedModel:
             raise RuntimeError("Attempting to train stock model")
-        shutil.copyfile(self.outputSamFile, tempSamFile)
+        hmmFile = None
         if doEm:
             hmmFile = self.emptyHmmFile
         elif useTrainedModel:
             hmmFile = trainedModelPath(trainedModelFile, self.getGlobalTempDir())
-        else:
-            hmmFile = None
-        self.addChildTargetFn(realignSamFileTargetFn, args=(tempSamFile, self.outputSamFile, self.readFastqFile,
-                                                            self.referenceFastaFile, gapGamma, matchGamma, hmmFile, doEm))
+        self.addChildTargetFn(realignSamFileTargetFn,
+                              args=(self._scratch_copy(self.getGlobalTempDir()), self.outputSamFile, self.readFastqFile,
+                                    self.referenceFastaFile, gapGamma, matchGamma, hmmFile, doEm))
