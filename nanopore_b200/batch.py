@@ -34,20 +34,22 @@ def reverse_complement_codes(codes):
 
 
 def pack_ops(ops):
-    """[(code, length), ...] -> uint32 (length<<2)|code, merging neighbours of equal code."""
-    out = []
-    for code, ln in ops:
-        if ln <= 0:
-            continue
-        if out and out[-1][0] == code:
-            out[-1][1] += ln
-        else:
-            out.append([code, ln])
-    return np.array([(ln << 2) | code for code, ln in out], dtype=np.uint32)
+    """[(code, length), ...] -> uint32 (length<<2)|code, dropping empty ops and merging neighbours of equal code."""
+    a = np.asarray(ops, dtype=np.int64).reshape(-1, 2)
+    a = a[a[:, 1] > 0]
+    if len(a) == 0:
+        return np.zeros(0, dtype=np.uint32)
+    code, ln = a[:, 0], a[:, 1]
+    first = np.concatenate(([True], code[1:] != code[:-1]))
+    if not first.all():
+        ln = np.add.reduceat(ln, np.flatnonzero(first))
+        code = code[first]
+    return ((ln << 2) | code).astype(np.uint32)
 
 
 def unpack_ops(packed):
-    return [(int(v) & 3, int(v) >> 2) for v in np.asarray(packed)]
+    p = np.asarray(packed, dtype=np.int64)
+    return list(zip((p & 3).tolist(), (p >> 2).tolist()))
 
 
 

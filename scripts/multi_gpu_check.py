@@ -31,12 +31,15 @@ def main():
     one.set_reference(b.ref)
     t0 = time.perf_counter(); ops1, off1, _ = one.realign(b, p); t1 = time.perf_counter() - t0
     pe = capi.default_params(band=10, split_side=300)
-    st1 = one.expectations(b, pe)
+    st1 = one.expectations(b, pe)                      # warm-up (allocations)
+    t0 = time.perf_counter(); st1 = one.expectations(b, pe); e1 = time.perf_counter() - t0
     one.close()
     sr = parallel.ShardedRealigner(hmm)
     sr.set_reference(b.ref)
     t0 = time.perf_counter(); opsN, offN, _ = sr.realign(b, p); tN = time.perf_counter() - t0
-    stN = sr.expectations(b, pe)
+    stN = sr.expectations(b, pe)                       # warm-up
+    t0 = time.perf_counter(); stN = sr.expectations(b, pe); eN = time.perf_counter() - t0
+    t0 = time.perf_counter(); opsN, offN, _ = sr.realign(b, p); tN = time.perf_counter() - t0
     sr.close()
     parallel.shutdown()
     ok = bool(np.array_equal(ops1, opsN) and np.array_equal(off1, offN) and st1 == stN)
@@ -44,7 +47,8 @@ def main():
     print(json.dumps({"multi_gpu_check": "OK" if ok else "MISMATCH", "world": world, "reads": n, "cigar_ops": int(len(ops1)),
                       "cells": int(sr.cells), "shard_sizes": [int(len(s)) for s in shards],
                       "shard_cost": [int(parallel.read_cost(b)[s].sum()) for s in shards],
-                      "loglik": float(stN.values()[105]), "t_single_s": round(t1, 3), "t_sharded_s": round(tN, 3)}), flush=True)
+                      "loglik": float(stN.values()[105]), "t_single_s": round(t1, 3), "t_sharded_s": round(tN, 3),
+                      "estep_single_s": round(e1, 3), "estep_sharded_s": round(eN, 3)}), flush=True)
     if not ok:
         sys.exit(1)
 
