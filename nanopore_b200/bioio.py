@@ -96,9 +96,10 @@ def fastqRead(fileHandleOrFile):
                                     "qual values (%s) for sequence: %s, ignoring returning None", len(seq), len(quals), name)
                     qv = None
                 else:
-                    qv = [ord(c) for c in quals]
-                    if any(q < 33 or q > 126 for q in qv):
+                    raw = quals.encode("latin-1")
+                    if raw and (min(raw) < 33 or max(raw) > 126):
                         raise RuntimeError("Got a qual value out of range for sequence %s" % name)
+                    qv = list(raw)
                 yield name, seq, qv
             line = fh.readline()
     finally:

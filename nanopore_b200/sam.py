@@ -18,15 +18,11 @@ _QUERY_CONSUMING = (BAM_CMATCH, BAM_CINS, BAM_CEQUAL, BAM_CDIFF)
 def parse_cigar(s):
     if s == "*" or s == "":
         return None
-    out, pos = [], 0
-    for m in _CIGAR_TOKEN.finditer(s):
-        if m.start() != pos:
-            raise ValueError("malformed CIGAR %r" % s)
-        out.append((_OP_CODE[m.group(2)], int(m.group(1))))
-        pos = m.end()
-    if pos != len(s):
+    toks = _CIGAR_TOKEN.findall(s)
+    if sum(len(n) for n, _ in toks) + len(toks) != len(s):          # every character belongs to a <number><op> token
         raise ValueError("malformed CIGAR %r" % s)
-    return tuple(out)
+    code = _OP_CODE
+    return tuple([(code[op], int(n)) for n, op in toks])
 
 
 def format_cigar(cigar):
