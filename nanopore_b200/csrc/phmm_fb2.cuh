@@ -107,7 +107,7 @@ struct Tabs {
 };
 
 // One column of 5 state values.  GUARD: scalar loads through an in-band test (any buffer, any stride);
-// otherwise two 16-byte and one 8-byte load from a CS-strided shared-memory column whose out-of-band
+// otherwise unguarded loads (16-byte ones when the columns are padded, CS = 6) from a CS-strided shared-memory column whose out-of-band
 // neighbours are kept at -inf.
 struct ColV { double M, sX, sY, lX, lY; };
 
