@@ -12,6 +12,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/phmm.h"
@@ -800,41 +801,64 @@ int phmm_batch_fetch(phmm_ctx *ctx, uint32_t **out_cigar_ops, int64_t **out_ciga
             }
             CK(cudaStreamSynchronize(ctx->stream));
         }
-        // CIGAR assembly: reference-only gap (D) before read-only gap (I) between matched runs
-        std::vector<uint32_t> ops;
+        // CIGAR assembly: reference-only gap (D) before read-only gap (I) between matched runs.  Reads are
+        // independent: a counting pass and a writing pass, both spread over the host threads.
         std::vector<int64_t> off(b.n_reads + 1, 0);
-        auto push = [&](int code, int64_t len, size_t first) {
-            while (len > 0) {
-                if (ops.size() > first && (int)(ops.back() & 3) == code && (ops.back() >> 2) + len <= 0x3fffffff) {
-                    ops.back() = (uint32_t)((((ops.back() >> 2) + len) << 2) | code);
-                    return;
+        // emits the ops of read r through `put(op)`; `last` carries the previous op for merging equal codes
+        auto assemble = [&](int64_t r, auto &&put) {
+            uint32_t cur = 0; bool have = false;
+            auto push = [&](int code, int64_t len) {
+                while (len > 0) {
+                    if (have && (int)(cur & 3) == code && (int64_t)(cur >> 2) + len <= 0x3fffffff) {
+                        cur = (uint32_t)((((int64_t)(cur >> 2) + len) << 2) | code);
+                        return;
+                    }
+                    if (have) put(cur);
+                    const int64_t l = std::min<int64_t>(len, 0x3fffffff);
+                    cur = (uint32_t)((l << 2) | code); have = true;
+                    len -= l;
                 }
-                const int64_t l = std::min<int64_t>(len, 0x3fffffff);
-                ops.push_back((uint32_t)((l << 2) | code));
-                len -= l;
-            }
-        };
-        for (int64_t r = 0; r < b.n_reads; r++) {
-            const size_t first = ops.size();
+            };
             int64_t pxx = -1, pyy = -1;
             for (int64_t g = b.read_first_region[r]; g < b.read_first_region[r + 1]; g++) {
                 const Region &reg = b.regions[g];
                 for (int64_t k = moff[g + 1] - 1; k >= moff[g]; k--) {       // stored in reverse
                     const int64_t x = reg.x1 + hx[k], y = reg.y1 + hy[k], n = hn[k];
-                    push(2, x - pxx - 1, first);
-                    push(1, y - pyy - 1, first);
-                    push(0, n, first);
+                    push(2, x - pxx - 1);
+                    push(1, y - pyy - 1);
+                    push(0, n);
                     pxx = x + n - 1; pyy = y + n - 1;
                 }
             }
-            push(2, b.read_lx[r] - pxx - 1, first);
-            push(1, b.read_ly[r] - pyy - 1, first);
-            off[r + 1] = (int64_t)ops.size();
-        }
-        *out_cigar_ops = (uint32_t *)xmalloc(ops.size() * 4);
+            push(2, b.read_lx[r] - pxx - 1);
+            push(1, b.read_ly[r] - pyy - 1);
+            if (have) put(cur);
+        };
+        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, std::thread::hardware_concurrency()), b.n_reads / 256));
+        auto parallel_reads = [&](auto &&fn) {
+            if (nthr <= 1) { fn(0, b.n_reads); return; }
+            std::vector<std::thread> th;
+            const int64_t chunk = (b.n_reads + nthr - 1) / nthr;
+            for (int t = 0; t < nthr; t++) {
+                const int64_t r0 = t * chunk, r1 = std::min<int64_t>(b.n_reads, r0 + chunk);
+                if (r0 < r1) th.emplace_back([&fn, r0, r1]() { fn(r0, r1); });
+            }
+            for (auto &t : th) t.join();
+        };
+        parallel_reads([&](int64_t r0, int64_t r1) {
+            for (int64_t r = r0; r < r1; r++) { int64_t c = 0; assemble(r, [&](uint32_t) { c++; }); off[r + 1] = c; }
+        });
+        for (int64_t r = 0; r < b.n_reads; r++) off[r + 1] += off[r];
+        const int64_t total_ops = off[b.n_reads];
+        *out_cigar_ops = (uint32_t *)xmalloc((size_t)total_ops * 4);
         *out_cigar_off = (int64_t *)xmalloc(off.size() * 8);
         if (!*out_cigar_ops || !*out_cigar_off) return fail(ctx, PHMM_E_NOMEM, "host allocation failed");
-        if (!ops.empty()) memcpy(*out_cigar_ops, ops.data(), ops.size() * 4);
+        {
+            uint32_t *const dst = *out_cigar_ops;
+            parallel_reads([&](int64_t r0, int64_t r1) {
+                for (int64_t r = r0; r < r1; r++) { uint32_t *w = dst + off[r]; assemble(r, [&](uint32_t v) { *w++ = v; }); }
+            });
+        }
         memcpy(*out_cigar_off, off.data(), off.size() * 8);
         int64_t tp = 0;
         for (int64_t i = 0; i < nreg; i++) tp += npairs[i];
