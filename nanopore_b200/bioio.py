@@ -14,6 +14,8 @@ import logging
 import re
 import subprocess
 
+import numpy as np
+
 logger = logging.getLogger("nanopore_b200")
 
 _COMPLEMENT = str.maketrans("ACGTNacgtn", "TGCANtgcan")
@@ -97,7 +99,8 @@ def fastqRead(fileHandleOrFile):
                     qv = None
                 else:
                     raw = quals.encode("latin-1")
-                    if raw and (min(raw) < 33 or max(raw) > 126):
+                    q8 = np.frombuffer(raw, dtype=np.uint8)
+                    if len(q8) and (q8.min() < 33 or q8.max() > 126):
                         raise RuntimeError("Got a qual value out of range for sequence %s" % name)
                     qv = list(raw)
                 yield name, seq, qv

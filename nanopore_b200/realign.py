@@ -85,27 +85,31 @@ def getAbsoluteReadOffset(alignedRead, refSeq, readSeq):
 # ---------------------------------------------------------------------------------------------------------
 # chaining (the step immediately before the path; defines its input shape)
 # ---------------------------------------------------------------------------------------------------------
+def _readOffsetFromArrays(aR, codes, lens, readSeq):
+    """getAbsoluteReadOffset on the array form of the cigar."""
+    readOffset = int(lens[0]) if len(codes) and codes[0] == 5 else 0
+    if aR.is_reverse:
+        readOffset = -(len(readSeq) - 1 - readOffset)
+    nc = codes != 5
+    c2, l2 = codes[nc], lens[nc]
+    return readOffset + (int(l2[0]) if len(c2) and c2[0] == 4 else 0)
+
+
 def _hit_summary(aR, refSeq, readSeq):
     """(aligned pair count, refPos first, signed readPos first, refPos last, signed readPos last): what the
-    reference derives by materialising AlignedPair.iterator (utils.py:388-396)."""
-    off = getAbsoluteReadOffset(aR, refSeq, readSeq)
-    q, r, n = 0, aR.pos, 0
-    first = last = None
-    for op, ln in aR.cigar:
-        if op == 0:
-            if first is None:
-                first = (r, off + q)
-            last = (r + ln - 1, off + q + ln - 1)
-            n += ln
-            q += ln
-            r += ln
-        elif op == 1:
-            q += ln
-        elif op == 2:
-            r += ln
-    if first is None:
+    reference derives by materialising AlignedPair.iterator (utils.py:388-396).  Works on the array form of the
+    cigar (prefix sums instead of a loop over ops)."""
+    codes, lens = aR.cigar_arrays()
+    off = _readOffsetFromArrays(aR, codes, lens, readSeq)
+    m = codes == 0
+    if not m.any():
         raise RuntimeError("alignment of %s has no aligned positions" % aR.qname)
-    return n, first[0], first[1], last[0], last[1]
+    qadv = np.where((codes == 0) | (codes == 1), lens, 0)
+    radv = np.where((codes == 0) | (codes == 2), lens, 0)
+    q0 = np.cumsum(qadv) - qadv                      # query / reference position at the start of each op
+    r0 = aR.pos + np.cumsum(radv) - radv
+    i0, i1 = np.flatnonzero(m)[[0, -1]]
+    return (int(lens[m].sum()), int(r0[i0]), off + int(q0[i0]), int(r0[i1] + lens[i1] - 1), off + int(q0[i1] + lens[i1] - 1))
 
 
 def chainFn(alignedReads, refSeq, readSeq, scoreFn=None, maxGap=200):
@@ -136,51 +140,57 @@ def chainFn(alignedReads, refSeq, readSeq, scoreFn=None, maxGap=200):
 
 def mergeChainedAlignedReads(chainedAlignedReads, refSequence, readSequence):
     """One global alignment for the chain (utils.py:295-386): pos = 0, seq = the read (reverse complemented for a
-    reverse-strand chain), leading/trailing D and I so that the cigar spans the whole reference and read."""
+    reverse-strand chain), leading/trailing D and I so that the cigar spans the whole reference and read.  The ops
+    are assembled as arrays; `cAR.cigar` materialises the tuple form on demand."""
     cAR = AlignedRead()
-    aR = chainedAlignedReads[0]
-    cAR.qname = aR.qname
+    first = chainedAlignedReads[0]
+    cAR.qname = first.qname
     cAR.rnext = -1
     cAR.pos = 0
-    cAR.is_reverse = aR.is_reverse
+    cAR.is_reverse = first.is_reverse
     cAR.seq = reverseComplement(readSequence) if cAR.is_reverse else readSequence
-    cAR.rname = aR.rname
-    cigarList = []
-    pPos = 0
-    pQPos = -(len(readSequence) - 1) if cAR.is_reverse else 0
+    cAR.rname = first.rname
+    code_parts, len_parts = [], []
+
+    def gap(code, length):
+        code_parts.append(np.array([code], dtype=np.uint8))
+        len_parts.append(np.array([length], dtype=np.int64))
+
+    pPos = 0                                                 # reference positions covered so far
+    pQPos = -(len(readSequence) - 1) if cAR.is_reverse else 0   # signed read position reached so far
     for aR in chainedAlignedReads:
         assert cAR.is_reverse == aR.is_reverse
         assert aR.pos >= pPos
-        if aR.pos > pPos:                                   # preceding unaligned reference positions
-            cigarList.append((2, aR.pos - pPos))
+        if aR.pos > pPos:                                    # unaligned reference positions before this hit
+            gap(2, aR.pos - pPos)
             pPos = aR.pos
-        qPos = getAbsoluteReadOffset(aR, refSequence, readSequence)
+        codes, lens = aR.cigar_arrays()
+        assert np.isin(codes, (0, 1, 2, 4, 5)).all()
+        qPos = _readOffsetFromArrays(aR, codes, lens, readSequence)
         assert qPos >= pQPos
-        if qPos > pQPos:                                    # preceding unaligned read positions
-            cigarList.append((1, qPos - pQPos))
+        if qPos > pQPos:                                     # unaligned read positions before this hit
+            gap(1, qPos - pQPos)
             pQPos = qPos
-        for op, length in aR.cigar:                         # the hit's own ops, clipping filtered
-            assert op in (0, 1, 2, 4, 5)
-            if op in (0, 1, 2):
-                cigarList.append((op, length))
-            if op in (0, 2):
-                pPos += length
-            if op in (0, 1):
-                pQPos += length
+        keep = codes <= 2                                    # the hit's own ops, clipping filtered
+        code_parts.append(codes[keep])
+        len_parts.append(lens[keep])
+        pPos += int(lens[(codes == 0) | (codes == 2)].sum())
+        pQPos += int(lens[(codes == 0) | (codes == 1)].sum())
     assert pPos <= len(refSequence)
     if pPos < len(refSequence):
-        cigarList.append((2, len(refSequence) - pPos))
+        gap(2, len(refSequence) - pPos)
     if cAR.is_reverse:
         assert pQPos <= 1
         if pQPos < 1:
-            cigarList.append((1, -pQPos + 1))
+            gap(1, -pQPos + 1)
     else:
         assert pQPos <= len(readSequence)
         if pQPos < len(readSequence):
-            cigarList.append((1, len(readSequence) - pQPos))
-    assert sum(length for op, length in cigarList if op in (0, 2)) == len(refSequence)
-    assert sum(length for op, length in cigarList if op in (0, 1)) == len(readSequence)
-    cAR.cigar = tuple(cigarList)
+            gap(1, len(readSequence) - pQPos)
+    codes, lens = np.concatenate(code_parts), np.concatenate(len_parts)
+    assert int(lens[(codes == 0) | (codes == 2)].sum()) == len(refSequence)
+    assert int(lens[(codes == 0) | (codes == 1)].sum()) == len(readSequence)
+    cAR.set_cigar_arrays(codes, lens)
     return cAR
 
 
@@ -234,16 +244,23 @@ def packAlignedReads(alignedReads, sam, packedRef):
         rn = sam.getrname(aR.rname)
         if rn not in packedRef.offset:
             raise RuntimeError("Reference sequence %s of read %s not in the reference fasta" % (rn, aR.qname))
-        for op, _ in aR.cigar:
-            assert op in (0, 1, 2, 4, 5)
-        o = pack_ops([(op, ln) for op, ln in aR.cigar if op in (0, 1, 2)])
-        q = aR.query
-        if aR.aend > packedRef.length[rn]:
+        codes, lens = aR.cigar_arrays()                      # no per-op Python work
+        assert np.isin(codes, (0, 1, 2, 4, 5)).all()
+        keep = codes <= 2
+        o = pack_ops(np.stack([codes[keep].astype(np.int64), lens[keep]], axis=1))
+        # aR.query / aR.aend from the arrays: soft clips bound the query, M and D consume the reference
+        seq = aR.seq or ""
+        nclip = codes != 5
+        c2, l2 = codes[nclip], lens[nclip]
+        qstart = int(l2[0]) if len(c2) and c2[0] == 4 else 0
+        qend = len(seq) - (int(l2[-1]) if len(c2) > 1 and c2[-1] == 4 else 0)
+        aend = aR.pos + int(lens[(codes == 0) | (codes == 2)].sum())
+        if aend > packedRef.length[rn]:
             raise RuntimeError("Alignment of %s runs past the end of %s" % (aR.qname, rn))
-        reads.append(encode(q))
+        reads.append(encode(seq[qstart:qend]))
         ops.append(o)
         rs.append(packedRef.offset[rn] + aR.pos)
-        re_.append(packedRef.offset[rn] + aR.aend)
+        re_.append(packedRef.offset[rn] + aend)
         names.append(aR.qname)
     read_off = np.concatenate(([0], np.cumsum([len(r) for r in reads]))).astype(np.int64)
     in_off = np.concatenate(([0], np.cumsum([len(o) for o in ops]))).astype(np.int64)
@@ -310,7 +327,7 @@ def realignSamFile2TargetFn(target, samFile, outputSamFile, readFastqFile, refer
     finally:
         realigner.close()
     assert len(off) == len(records) + 1                    # exactly one cigar per read (utils.py:588-589)
-    cigars = [tuple(unpack_ops(ops[off[i]:off[i + 1]])) for i in range(len(records))]
+    cigars = [ops[off[i]:off[i + 1]] for i in range(len(records))]          # packed uint32, see realignSamFile3TargetFn
     target.logToMaster("Realigned %d reads (%d DP cells) from %s" % (len(records), getattr(realigner, "cells", 0), samFile))
     realignSamFile3TargetFn(target, samFile, outputSamFile, cigars)
 
@@ -336,13 +353,17 @@ def realignCigarTargetFn(target, exonerateCigarString, referenceSequenceName, re
 
 
 def realignSamFile3TargetFn(target, samFile, outputSamFile, cigars):
-    """Fan-in (utils.py:591-609): replaces each mapped record's cigar, input order, header copied.  `cigars` is the
-    list of (op, length) tuples per mapped record (the reference reads them back from one temp file per read)."""
+    """Fan-in (utils.py:591-609): replaces each mapped record's cigar, input order, header copied.  `cigars` holds,
+    per mapped record, either a sequence of (op, length) tuples or a packed uint32 array (length << 2 | op) as the
+    library returns it (the reference reads the ops back from one temp cigar file per read)."""
     sam = Samfile(samFile, "r")
     outputSam = Samfile(outputSamFile, "wh", template=sam)
     n = 0
     for aR, cigar in zip(samIterator(sam), cigars):
-        aR.cigar = tuple((int(op), int(length)) for op, length in cigar)
+        if isinstance(cigar, np.ndarray) and cigar.dtype == np.uint32:
+            aR.set_cigar_arrays(cigar & 3, cigar >> 2)
+        else:
+            aR.cigar = tuple((int(op), int(length)) for op, length in cigar)
         outputSam.write(aR)
         n += 1
     assert n == len(cigars)

@@ -7,6 +7,8 @@ aligned_pairs, rnext (utils.py:168-180,295-386,487-506,557-609).  Coordinates ar
 """
 import re
 
+import numpy as np
+
 BAM_CMATCH, BAM_CINS, BAM_CDEL, BAM_CREF_SKIP, BAM_CSOFT_CLIP, BAM_CHARD_CLIP, BAM_CPAD, BAM_CEQUAL, BAM_CDIFF = range(9)
 _OPS = "MIDNSHP=X"
 _OP_CODE = {c: i for i, c in enumerate(_OPS)}
@@ -31,6 +33,42 @@ def format_cigar(cigar):
     return "".join("%d%s" % (ln, _OPS[op]) for op, ln in cigar)
 
 
+_OP_LUT = np.full(256, 255, dtype=np.uint8)
+for _i, _c in enumerate(_OPS.encode()):
+    _OP_LUT[_c] = _i
+_OP_CHARS = np.array(list(_OPS))
+
+
+def parse_cigar_arrays(s):
+    """CIGAR text -> (op codes uint8, lengths int64) without building Python tuples (digits are combined with
+    positional weights in numpy).  Same validation as parse_cigar."""
+    if s == "*" or s == "":
+        return np.zeros(0, np.uint8), np.zeros(0, np.int64)
+    raw = np.frombuffer(s.encode("ascii"), dtype=np.uint8)
+    code_at = _OP_LUT[raw]
+    isop = code_at != 255
+    isdig = (raw >= 48) & (raw <= 57)
+    idx = np.flatnonzero(isop)
+    if len(idx) == 0 or not (isop | isdig).all() or not isop[-1]:
+        raise ValueError("malformed CIGAR %r" % s)
+    starts = np.concatenate(([0], idx[:-1] + 1))
+    if (idx == starts).any() or (idx - starts > 18).any():                       # an op without a number / absurd length
+        raise ValueError("malformed CIGAR %r" % s)
+    grp = np.cumsum(isop) - isop
+    expo = idx[grp] - 1 - np.arange(len(raw))
+    expo[isop] = 0
+    val = np.where(isop, 0, (raw.astype(np.int64) - 48) * 10 ** expo)
+    return code_at[idx], np.add.reduceat(val, starts)
+
+
+def format_cigar_arrays(codes, lens):
+    """(op codes, lengths) -> CIGAR text."""
+    if len(codes) == 0:
+        return "*"
+    parts = np.char.add(np.asarray(lens, dtype=np.int64).astype("U20"), _OP_CHARS[np.asarray(codes, dtype=np.int64)])
+    return "".join(parts.tolist())
+
+
 class AlignedRead:
     def __init__(self):
         self.qname = ""
@@ -38,13 +76,46 @@ class AlignedRead:
         self.rname = -1
         self.pos = -1
         self.mapq = 0
-        self.cigar = None
+        self._cigar = None         # tuple of (op, length), parsed on first use
+        self._cigar_s = None       # CIGAR text as read from the file (until .cigar is assigned)
+        self._cigar_a = None       # (text, arrays) cache of cigar_arrays()
         self.rnext = -1
         self.pnext = -1
         self.tlen = 0
         self.seq = ""
         self.qual = None
         self.tags = []            # raw "TAG:TYPE:VALUE" strings, passed through
+
+    # ---- cigar: text is parsed only when somebody looks at it ----
+    @property
+    def cigar(self):
+        if self._cigar is None and self._cigar_s is not None:
+            self._cigar = parse_cigar(self._cigar_s)
+            self._cigar_s = None
+        return self._cigar
+
+    @cigar.setter
+    def cigar(self, value):
+        self._cigar = tuple(value) if value is not None else None
+        self._cigar_s = None
+
+    def cigar_arrays(self):
+        """(op codes uint8, lengths int64); straight from the text when the tuple form was never needed."""
+        if self._cigar is None and self._cigar_s is not None:
+            if self._cigar_a is None or self._cigar_a[0] is not self._cigar_s:
+                self._cigar_a = (self._cigar_s, parse_cigar_arrays(self._cigar_s))     # parsed once per text
+            return self._cigar_a[1]
+        c = self._cigar or ()
+        a = np.asarray(c, dtype=np.int64).reshape(-1, 2)
+        return a[:, 0].astype(np.uint8), a[:, 1]
+
+    def set_cigar_arrays(self, codes, lens):
+        """Assigns the cigar from arrays; the tuple form is only built if somebody asks for it."""
+        self._cigar = None
+        self._cigar_s = format_cigar_arrays(codes, lens)
+
+    def cigar_text(self):
+        return self._cigar_s if self._cigar is None and self._cigar_s is not None else format_cigar(self._cigar)
 
     # ---- flags ----
     @property
@@ -207,7 +278,7 @@ class Samfile:
         a.qname, a.flag = f[0], int(f[1])
         a.rname = self._tid_of(f[2])
         a.pos, a.mapq = int(f[3]) - 1, int(f[4])
-        a.cigar = parse_cigar(f[5])
+        a._cigar_s = None if f[5] in ("*", "") else f[5]
         a.rnext = a.rname if f[6] == "=" else self._tid_of(f[6])
         a.pnext, a.tlen = int(f[7]) - 1, int(f[8])
         a.seq = "" if f[9] == "*" else f[9]
@@ -223,7 +294,7 @@ class Samfile:
             rnext = "="
         else:
             rnext = self.references[a.rnext]
-        fields = [a.qname, str(a.flag), rn, str(a.pos + 1), str(a.mapq), format_cigar(a.cigar), rnext,
+        fields = [a.qname, str(a.flag), rn, str(a.pos + 1), str(a.mapq), a.cigar_text(), rnext,
                   str(a.pnext + 1), str(a.tlen), a.seq if a.seq else "*", a.qual if a.qual else "*"]
         fields.extend(a.tags)
         self._fh.write("\t".join(fields) + "\n")
