@@ -18,7 +18,8 @@ from nanopore_b200.mappers.abstractMapper import AbstractMapper     # noqa: E402
 from nanopore_b200.target import Stack                              # noqa: E402
 
 
-def main(argv=None):
+def main(argv=None, local_factory=None):
+    """local_factory: what each rank uses to realign its shard (default: the GPU Realigner of that rank)."""
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("sam"); ap.add_argument("reads_fastq"); ap.add_argument("reference_fasta"); ap.add_argument("out_sam")
     ap.add_argument("--gapGamma", type=float, default=0.5)
@@ -40,7 +41,7 @@ def main(argv=None):
             raise RuntimeError("%d job(s) failed" % failed)         # nanopore/pipeline.py:209-210
         return 0
 
-    return parallel.run(work)
+    return parallel.run(work, local_factory)
 
 
 if __name__ == "__main__":

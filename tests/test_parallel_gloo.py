@@ -63,3 +63,33 @@ def test_world_size_2_matches_single_rank(tmp_path):
     ops2, off2, _ = r.realign(b, p)
     assert got["ops_trained"] == ops2.tolist() and got["off_trained"] == off2.tolist()
     assert got["ops_trained"] != got["ops"]                              # the broadcast model was really used
+
+
+def test_command_line_under_two_ranks_writes_the_single_process_sam(tmp_path):
+    """scripts/realign_sam.py under world_size 2 (parallel.run: rank 0 runs the pipeline, rank 1 serves): the SAM it
+    writes is byte-identical to a single-process run, including a trained model broadcast to the other rank."""
+    import filecmp
+    import importlib.util
+    from nanopore_b200 import realign
+    from helpers_sam import make_experiment
+    ref_fa, fq, sam_path, _ = make_experiment(str(tmp_path), n_reads=7, read_len=350, seed=23)
+    out2 = str(tmp_path / "out_2ranks.sam")
+    port = free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_dist_cli_worker.py"), sam_path, fq, ref_fa, out2,
+                                       "--trained", "blasr_hmm_40.txt"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        o, _ = p.communicate(timeout=300)
+        assert p.returncode == 0, o
+    spec = importlib.util.spec_from_file_location("realign_sam", os.path.join(os.path.dirname(HERE), "scripts", "realign_sam.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out1 = str(tmp_path / "out_1rank.sam")
+    prev = realign.setRealignerFactory(oracle_realigner_factory())
+    try:
+        assert mod.main([sam_path, fq, ref_fa, out1, "--trained", "blasr_hmm_40.txt"]) == 0
+    finally:
+        realign.setRealignerFactory(prev)
+    assert filecmp.cmp(out1, out2, shallow=False)
