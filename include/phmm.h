@@ -182,7 +182,8 @@ int phmm_set_memory_budget(phmm_ctx *ctx, int64_t bytes);
  *   "smem_columns"  0 = choose, else the shared-memory diagonal buffer (power of two, 64..1024)
  *   "timing_experiment" bit mask that SKIPS parts of the windowed kernel to time the rest (1 forward sequence
  *                      loads, 2 forward ring stores, 16 traceback windows, 32 forward cells, 64 totals,
- *                      128 posteriors, 256 backward cells).  Results are WRONG when non-zero; used only by
+ *                      128 posteriors, 256 backward cells; 512 is harmless: posterior phase re-reads every cell
+ *                      instead of the candidates collected during the backward sweep).  Results are WRONG when non-zero; used only by
  *                      scripts/tune.py for the phase breakdown in profiles/.  0 (default) = the real kernel.
  * Returns PHMM_E_ARG for an unknown name or value. */
 int phmm_set_option(phmm_ctx *ctx, const char *name, int64_t value);

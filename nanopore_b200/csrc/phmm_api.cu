@@ -64,6 +64,7 @@ struct BatchState {
     std::vector<int64_t> tb_off;              // n_regions + 1
     std::vector<int64_t> rec_off;             // n_regions + 1: first diagonal record of each region
     int64_t ring_doubles = 0; int32_t wcap = 0, wg = 0, tcap = 0;
+    int32_t ccap = 1;                            // posterior candidates per slot (k_fb2)
     int32_t cell_doubles = 1, total_extra = 5;   // ring doubles per cell / extra on total-probability diagonals
     size_t fb2_smem = 0;
     phmm_batch_stats stats;
@@ -85,7 +86,7 @@ struct phmm_ctx {
     DevBuf d_ref; int64_t ref_len = -1;
     DevBuf d_reads, d_regions, d_runs, d_geom, d_order, d_counter;
     DevBuf d_fring, d_dtab, d_bring, d_dots;
-    DevBuf d_tboff, d_tbp, d_ring, d_wide, d_fsave, d_totals, d_recs, d_recoff;
+    DevBuf d_tboff, d_tbp, d_ring, d_wide, d_fsave, d_totals, d_recs, d_recoff, d_cand;
     DevBuf d_px, d_py, d_pw, d_npairs;
     DevBuf d_expT, d_expE, d_expLL;
     DevBuf d_sumx, d_sumy, d_dstart, d_dfill, d_sidx, d_wre, d_pred, d_colmap, d_sring, d_lring;
@@ -360,7 +361,7 @@ int plan_memory(phmm_ctx *ctx) {
         occ = fb2_occupancy(b.nw, sw, b.expect, b.fb2_smem);
         if (occ < 1) return fail(ctx, PHMM_E_CUDA, "k_fb2 does not fit on this device");
         slot_bytes = b.ring_doubles * 8 + (int64_t)4 * NS * b.wg * 8 +
-                     (int64_t)2 * CS * b.wcap * 8 + ((int64_t)b.tcap + b.wg) * 8;
+                     (int64_t)2 * CS * b.wcap * 8 + ((int64_t)b.tcap + b.wg) * 8 + (b.expect ? 8 : (2 * (int64_t)b.max_pairs + 1024) * 8);
     } else {
         b.nw = avgw <= 40.0 ? 1 : (avgw <= 96.0 ? 2 : 4);
         occ = b.nw == 1 ? occupancy_fwdbwd<1>(sw, b.expect) : b.nw == 2 ? occupancy_fwdbwd<2>(sw, b.expect) : occupancy_fwdbwd<4>(sw, b.expect);
@@ -392,6 +393,8 @@ int plan_memory(phmm_ctx *ctx) {
         CK(ctx->d_wide.ensure((size_t)want * 4 * NS * b.wg * 8));
         CK(ctx->d_fsave.ensure((size_t)want * 2 * CS * b.wcap * 8));
         CK(ctx->d_totals.ensure((size_t)want * ((size_t)b.tcap + b.wg) * 8));
+        b.ccap = b.expect ? 1 : 2 * b.max_pairs + 1024;
+        CK(ctx->d_cand.ensure((size_t)want * (size_t)b.ccap * 8));
     } else {
         ctx->d_ring.release(); ctx->d_wide.release(); ctx->d_recs.release();
         CK(ctx->d_dtab.ensure((size_t)want * b.dcap * sizeof(DiagRec)));
@@ -556,6 +559,7 @@ int do_run(phmm_ctx *ctx) {
         f2.wide = ctx->d_wide.as<double>(); f2.wg = b.wg;
         f2.fsave = ctx->d_fsave.as<double>(); f2.totals = ctx->d_totals.as<double>(); f2.tcap = b.tcap;
         f2.wcap = b.wcap;
+        f2.cand = ctx->d_cand.as<long long>(); f2.ccap = b.ccap;
         f2.dbg = ctx->opt_dbg;
         f2.px = fa.px; f2.py = fa.py; f2.pw = fa.pw; f2.npairs = fa.npairs;
         f2.expT = fa.expT; f2.expE = fa.expE; f2.expLL = fa.expLL;

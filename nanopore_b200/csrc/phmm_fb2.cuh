@@ -66,6 +66,7 @@ struct Fb2Args {
     double *wide;   int32_t wg;  // 4 x wg x 5 doubles: F even/odd, B even/odd for diagonals wider than wcap
     double *fsave;               // 2 x wcap x CS doubles: forward state across a traceback window
     double *totals; int32_t tcap; // per slot: tcap totals, then wg sums F_M + B_M of the diagonal just above the posterior range
+    long long *cand; int32_t ccap; // per slot: posterior candidates (diagonal << 32 | cell) of the current window
     int32_t wcap;                // shared-memory columns (power of two)
     // outputs
     int32_t *px, *py, *pw;
@@ -323,6 +324,9 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
     DiagRec *const srec = reinterpret_cast<DiagRec *>(sct + FB2_TAB);            // [2][FB2_RQ]
     __shared__ int s_region;
     __shared__ int s_npairs;
+    __shared__ double s_est;                           // total of the window's first posterior diagonal
+    __shared__ int s_ncand, s_estok;
+    constexpr double EST_EPS = 0.02;                   // how far a window's totals may lie from s_est (verified per window)
     __shared__ EmisTables etab;                        // EXPECT
     __shared__ unsigned long long sT[EXPECT ? 25 : 1];
     __shared__ unsigned long long sE[EXPECT ? 80 : 1];
@@ -359,6 +363,8 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
     double *const fsave = a.fsave + (int64_t)slot * 2 * CS * wcap;
     double *const totals = a.totals + (int64_t)slot * (a.tcap + a.wg);
     double *const ovs = totals + a.tcap;
+    long long *const cand = a.cand + (int64_t)slot * a.ccap;
+    const double lp_lo = a.p.lp_skip - EST_EPS;
     const int wgmask = a.wg - 1;
     const int tbd = a.p.tb_diags + 1;
 
@@ -376,6 +382,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
         }
     };
     // every column of buffer `par` outside [clo, clo + w) (band columns, unwrapped; w <= wcap)
+    auto rg_of = [&](const DiagRec &r) -> double * { return ring + r.off; };
     auto clear_outside = [&](int par, int clo, int w, int lane, int nthr) { clear_cols(par, clo + w, clo + wcap - 1, lane, nthr); };
 
     for (;;) {
@@ -514,6 +521,8 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                     if (!at_end) {
                         for (int i = tid; i < 2 * CS * wcap; i += NTA) fsave[i] = sbuf[i];
                     }
+                    if (tid == 0) { s_ncand = 0; s_estok = 1; }
+                    double est = 0.0;                                                    // = s_est once the sweep has passed traced_from
                     DiagRec preb;                                                        // backward counterpart of `pre`
                     preb.off = preb.xlo = preb.w = preb.pad = 0;
                     if (tid < FB2_BATCH) {
@@ -566,6 +575,11 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                                             // diagonal once more, and only the one next to the range feeds a total
                                             if (dd <= traced_from) rg[i] = sM;
                                             else if (dd == traced_from + 1) ovs[i] = sM;
+                                            // posterior candidate: could reach the threshold for any total within EST_EPS of est
+                                            if (dd < traced_from && sM - est >= lp_lo) {
+                                                const int cs = atomicAdd(&s_ncand, 1);
+                                                if (cs < a.ccap) cand[cs] = ((long long)dd << 32) | (unsigned)i;
+                                            }
                                         }
                                         if (dots) {
                                             double t = sM;
@@ -603,6 +617,10 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                                         } else {
                                             if (dd <= traced_from) rg[i] = sM;
                                             else if (dd == traced_from + 1) ovs[i] = sM;
+                                            if (dd < traced_from && sM - est >= lp_lo) {
+                                                const int cs = atomicAdd(&s_ncand, 1);
+                                                if (cs < a.ccap) cand[cs] = ((long long)dd << 32) | (unsigned)i;
+                                            }
                                         }
                                         if (dots) {
                                             double t = sM;
@@ -622,6 +640,21 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                                     clear_outside(bpar, bclo, rb.w, tid, NC);
                                 }
                                 __syncthreads();
+                            }
+                            if (!EXPECT && dd == traced_from) {
+                                // the window's first total, evaluated as phase 2 will (same folds): the yardstick of the
+                                // candidate test for all diagonals below
+                                if (tid == 0) {
+                                    const double *cd = rg_of(rb) + DOT * rb.w;
+                                    double total = fold_seq(rb.w, ctab, [&](int i) { return cd[i]; });
+                                    if (dd < d) {
+                                        const int w1e = bw1;                         // width of diagonal dd+1 (previous iteration)
+                                        total = logadd_t(total, fold_seq(w1e, ctab, [&](int i) { return ovs[i]; }), ctab);
+                                    }
+                                    s_est = total;
+                                }
+                                __syncthreads();
+                                est = s_est;
                             }
                             bxlo2 = bxlo1; bw2 = bw1; bf2 = bf1;
                             bxlo1 = rb.xlo; bw1 = rb.w; bf1 = rb.pad;
@@ -643,6 +676,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                             total = logadd_t(total, t1, ctab);
                         }
                         totals[k] = total;
+                        if (!EXPECT && !(fabs(total - s_est) <= EST_EPS)) s_estok = 0;     // the candidate test was not safe: full scan
                     }
                     __syncthreads();
                     if (EXPECT) {
@@ -674,7 +708,42 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                         for (int k = 0; k < EXP_NT; k++)
                             if (accT[k]) atomicAdd(&sT[EXP_SLOT_TR[k]], accT[k]);
                     }
-                    // phase 3: posterior match probabilities, one warp per diagonal
+                    // phase 3: posterior match probabilities >= threshold.  When every total of the window lies within EST_EPS
+                    // of its first one (verified above), only the first diagonal and the candidates collected during the
+                    // backward sweep can pass; otherwise (or when the candidate list overflowed) every cell is re-read.
+                    auto emit = [&](int dd, int i, int xlo_, double sM, double total) {
+                        const int x = xlo_ + i, y = dd - x;
+                        if (x > 0 && y > 0) {
+                            const double lp = sM - total;
+                            if (lp >= a.p.lp_skip) {
+                                double pr = exp_det(lp);
+                                if (pr >= a.p.threshold) {
+                                    if (pr > 1.0) pr = 1.0;
+                                    const int wq = (int)floor(pr * (double)PROB_1);
+                                    const int slotp = atomicAdd(&s_npairs, 1);
+                                    if (slotp < reg.pair_cap) {
+                                        a.px[reg.pair_off + slotp] = x - 1;
+                                        a.py[reg.pair_off + slotp] = y - 1;
+                                        a.pw[reg.pair_off + slotp] = wq;
+                                    }
+                                }
+                            }
+                        }
+                    };
+                    const int ncand = s_ncand;
+                    if (!EXPECT && s_estok && ncand <= a.ccap && !(a.dbg & (128 | 512)) && traced_from > traced_to) {
+                        {
+                            const DiagRec r0 = rec[traced_from];
+                            const double *sm = ring + r0.off;
+                            for (int i = tid; i < r0.w; i += NC) emit(traced_from, i, r0.xlo, sm[i], totals[0]);
+                        }
+                        for (int c = tid; c < ncand; c += NC) {
+                            const long long v = cand[c];
+                            const int dd = (int)(v >> 32), i = (int)(unsigned)v;
+                            const DiagRec r0 = rec[dd];
+                            emit(dd, i, r0.xlo, ring[r0.off + i], totals[(traced_from - dd) / TOTAL_EVERY]);
+                        }
+                    } else
                     for (int dd = EXPECT ? traced_to : traced_from - (tid >> 5); dd > ((a.dbg & 128) ? traced_from : traced_to); dd -= NW) {
                         const DiagRec r0 = rec[dd];
                         const double total = totals[(traced_from - dd) / TOTAL_EVERY];
@@ -684,26 +753,8 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
 #pragma unroll
                             for (int u = 0; u < 4; u++) sv[u] = i0 + 32 * u < r0.w ? sm[i0 + 32 * u] : PHMM_NEG_INF;   // 4 loads in flight
 #pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                            const int i = i0 + 32 * u;
-                            const int x = r0.xlo + i, y = dd - x;
-                            if (i < r0.w && x > 0 && y > 0) {
-                                const double lp = sv[u] - total;
-                                if (lp >= a.p.lp_skip) {
-                                    double pr = exp_det(lp);
-                                    if (pr >= a.p.threshold) {
-                                        if (pr > 1.0) pr = 1.0;
-                                        const int wq = (int)floor(pr * (double)PROB_1);
-                                        const int slotp = atomicAdd(&s_npairs, 1);
-                                        if (slotp < reg.pair_cap) {
-                                            a.px[reg.pair_off + slotp] = x - 1;
-                                            a.py[reg.pair_off + slotp] = y - 1;
-                                            a.pw[reg.pair_off + slotp] = wq;
-                                        }
-                                    }
-                                }
-                            }
-                            }
+                            for (int u = 0; u < 4; u++)
+                                if (i0 + 32 * u < r0.w) emit(dd, i0 + 32 * u, r0.xlo, sv[u], total);
                         }
                     }
                     __syncthreads();
