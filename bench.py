@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = 4 x cores, about 15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="library option (phmm_set_option) for kernel experiments, e.g. register_path=0; recorded in config")
     return ap.parse_args()
 
 
@@ -224,6 +226,9 @@ def main():
         dist.broadcast(ref_t, src=0)
         assert np.array_equal(ref_t.cpu().numpy(), b.ref)
     ctx = capi.PhmmContext(local)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     stream = torch.cuda.Stream(device=dev)           # the library launches on this stream; the events below time it
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
@@ -305,7 +310,9 @@ def main():
                              "frac_of_datasheet_8TBs": achieved / 8000.0},
                 "clocks": clocks, "gpu_launches": launches,
                 "cells_per_read": cells_total / reads_total, "pairs": st["pairs"], "regions": st["n_regions"],
-                "decode_ms": dec_ms / args.steps}
+                "resident_regions": st["n_slots"], "decode_ms": dec_ms / args.steps}
+        if args.opt:
+            line["config"]["library_options"] = list(args.opt)
         if e2e_ms is not None:
             line["e2e"] = {"value": reads_total / (e2e_max * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d,
                            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_max}

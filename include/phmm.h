@@ -180,11 +180,11 @@ int phmm_set_memory_budget(phmm_ctx *ctx, int64_t bytes);
  *                      diagonals that hold no posterior pair; results are identical
  *   "warps"         0 = choose by band width, else 2, 4 or 8 warps per DP region
  *   "smem_columns"  0 = choose, else the shared-memory diagonal buffer (power of two, 64..1024)
- *   "timing_experiment" bit mask that SKIPS parts of the windowed kernel to time the rest (1 forward sequence
- *                      loads, 2 forward ring stores, 16 traceback windows, 32 forward cells, 64 totals,
- *                      128 posteriors, 256 backward cells; 512 is harmless: posterior phase re-reads every cell
- *                      instead of the candidates collected during the backward sweep).  Results are WRONG when non-zero; used only by
- *                      scripts/tune.py for the phase breakdown in profiles/.  0 (default) = the real kernel.
+ *   "candidate_cap" / "candidate_eps_ppm"  capacity and tolerance (1e-6 log units, default 20000) of the posterior
+ *                      candidate shortcut; tests use them to force its fall-backs; results are identical
+ *   "timing_experiment" non-zero is rejected by the shipped library.  A library built with -DPHMM_TUNE (scripts/tune.py
+ *                      builds one under build/) takes a bit mask that SKIPS parts of the windowed kernel to time the
+ *                      rest; its results are wrong by design and it is never loaded by nanopore_b200.
  * Returns PHMM_E_ARG for an unknown name or value. */
 int phmm_set_option(phmm_ctx *ctx, const char *name, int64_t value);
 

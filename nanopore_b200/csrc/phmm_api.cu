@@ -82,7 +82,8 @@ struct phmm_ctx {
     DevModel model;
     int64_t mem_budget = 0;
     bool force_legacy = false, decode_full_sweep = false;
-    int opt_warps = 0, opt_wcap = 0, opt_dbg = 0;             // tests: run the first-generation kernel (k_fwdbwd) instead of k_fb2
+    int opt_warps = 0, opt_wcap = 0, opt_dbg = 0, opt_ccap = 0;
+    double opt_est_eps = 0.02;             // tests: run the first-generation kernel (k_fwdbwd) instead of k_fb2
     DevBuf d_ref; int64_t ref_len = -1;
     DevBuf d_reads, d_regions, d_runs, d_geom, d_order, d_counter;
     DevBuf d_fring, d_dtab, d_bring, d_dots;
@@ -361,7 +362,7 @@ int plan_memory(phmm_ctx *ctx) {
         occ = fb2_occupancy(b.nw, sw, b.expect, b.fb2_smem);
         if (occ < 1) return fail(ctx, PHMM_E_CUDA, "k_fb2 does not fit on this device");
         slot_bytes = b.ring_doubles * 8 + (int64_t)4 * NS * b.wg * 8 +
-                     (int64_t)2 * CS * b.wcap * 8 + ((int64_t)b.tcap + b.wg) * 8 + (b.expect ? 8 : (2 * (int64_t)b.max_pairs + 1024) * 8);
+                     (int64_t)2 * CS * b.wcap * 8 + ((int64_t)b.tcap + b.wg) * 8 + (b.expect ? 8 : (ctx->opt_ccap > 0 ? (int64_t)ctx->opt_ccap : 2 * (int64_t)b.max_pairs + 1024) * 8);
     } else {
         b.nw = avgw <= 40.0 ? 1 : (avgw <= 96.0 ? 2 : 4);
         occ = b.nw == 1 ? occupancy_fwdbwd<1>(sw, b.expect) : b.nw == 2 ? occupancy_fwdbwd<2>(sw, b.expect) : occupancy_fwdbwd<4>(sw, b.expect);
@@ -393,7 +394,7 @@ int plan_memory(phmm_ctx *ctx) {
         CK(ctx->d_wide.ensure((size_t)want * 4 * NS * b.wg * 8));
         CK(ctx->d_fsave.ensure((size_t)want * 2 * CS * b.wcap * 8));
         CK(ctx->d_totals.ensure((size_t)want * ((size_t)b.tcap + b.wg) * 8));
-        b.ccap = b.expect ? 1 : 2 * b.max_pairs + 1024;
+        b.ccap = b.expect ? 1 : (ctx->opt_ccap > 0 ? ctx->opt_ccap : 2 * b.max_pairs + 1024);
         CK(ctx->d_cand.ensure((size_t)want * (size_t)b.ccap * 8));
     } else {
         ctx->d_ring.release(); ctx->d_wide.release(); ctx->d_recs.release();
@@ -559,7 +560,7 @@ int do_run(phmm_ctx *ctx) {
         f2.wide = ctx->d_wide.as<double>(); f2.wg = b.wg;
         f2.fsave = ctx->d_fsave.as<double>(); f2.totals = ctx->d_totals.as<double>(); f2.tcap = b.tcap;
         f2.wcap = b.wcap;
-        f2.cand = ctx->d_cand.as<long long>(); f2.ccap = b.ccap;
+        f2.cand = ctx->d_cand.as<long long>(); f2.ccap = b.ccap; f2.est_eps = ctx->opt_est_eps;
         f2.dbg = ctx->opt_dbg;
         f2.px = fa.px; f2.py = fa.py; f2.pw = fa.pw; f2.npairs = fa.npairs;
         f2.expT = fa.expT; f2.expE = fa.expE; f2.expLL = fa.expLL;
@@ -723,8 +724,18 @@ int phmm_set_option(phmm_ctx *ctx, const char *name, int64_t value) {
     else if (n == "warps") {
         if (value != 0 && value != 2 && value != 4 && value != 8) return fail(ctx, PHMM_E_ARG, "warps must be 0, 2, 4 or 8");
         ctx->opt_warps = (int)value;
+    } else if (n == "candidate_cap") {                 // tests: posterior candidates per window before the full re-read (0 = automatic)
+        if (value < 0 || value > 0x7fffffff) return fail(ctx, PHMM_E_ARG, "candidate_cap must be >= 0");
+        ctx->opt_ccap = (int)value;
+    } else if (n == "candidate_eps_ppm") {             // tests: tolerance of the candidate shortcut in 1e-6 log units (default 20000)
+        if (value < 0) return fail(ctx, PHMM_E_ARG, "candidate_eps_ppm must be >= 0");
+        ctx->opt_est_eps = (double)value * 1e-6;
     } else if (n == "timing_experiment") {
+#ifdef PHMM_TUNE
         ctx->opt_dbg = (int)value;
+#else
+        if (value != 0) return fail(ctx, PHMM_E_ARG, "timing_experiment exists only in a library built with -DPHMM_TUNE (scripts/tune.py)");
+#endif
     } else if (n == "smem_columns") {
         if (value != 0 && (value < 64 || value > 1024 || (value & (value - 1)))) return fail(ctx, PHMM_E_ARG, "smem_columns must be 0 or a power of two in [64, 1024]");
         ctx->opt_wcap = (int)value;

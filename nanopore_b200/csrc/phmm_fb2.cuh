@@ -36,6 +36,7 @@ namespace phmm {
 
 constexpr int FB2_RQ = 64;          // record FIFO entries (power of two): two batches
 constexpr int FB2_BATCH = 32;       // records streamed per refill (one per lane of the first warp)
+
 constexpr int REC_TOT = 1;          // DiagRec::pad bits: the window evaluates the total probability here
 constexpr int REC_WIDE = 2;         //   wider than the shared-memory buffer: lives in the global fallback buffer
 constexpr int REC_FAST3 = 4;        //   diagonals d-2, d-1, d (+-1 column) fit the shared-memory columns without aliasing
@@ -43,7 +44,18 @@ constexpr int REC_FAST3 = 4;        //   diagonals d-2, d-1, d (+-1 column) fit 
 #define PHMM_CS 5
 #endif
 constexpr int CS = PHMM_CS;               // doubles per shared-memory column: 5 (five resident regions per SM at 512 columns) or 6 (padded: 16-byte loads)
-constexpr int FB2_TAB = 16 + 25 * CS + 5 * CS + 5 * CS;   // logAdd coefficients + the three (emission + transition) tables
+constexpr int TS = 6;                     // doubles per row of the (emission + transition) tables: 5 used, 16-byte aligned pairs
+constexpr int TG_S = 0, TG_SS = 1, TG_L = 2, TG_LL = 3, TG_SW = 4;   // slots of a gap row: M->s, s->s, M->l, l->l, other s->s (switch)
+constexpr int FB2_TAB = 16 + 25 * TS + 5 * TS + 5 * TS;   // logAdd coefficients + the three (emission + transition) tables
+
+
+// Timing experiments (scripts/tune.py) switch phases of the kernel off and make its results wrong: they exist only in
+// a library built with -DPHMM_TUNE, never in the shipped one.
+#ifdef PHMM_TUNE
+#define FB2_DBG(bits) ((a.dbg & (bits)) != 0)
+#else
+#define FB2_DBG(bits) false
+#endif
 
 struct Fb2Args {
     const uint8_t *ref;
@@ -67,6 +79,7 @@ struct Fb2Args {
     double *fsave;               // 2 x wcap x CS doubles: forward state across a traceback window
     double *totals; int32_t tcap; // per slot: tcap totals, then wg sums F_M + B_M of the diagonal just above the posterior range
     long long *cand; int32_t ccap; // per slot: posterior candidates (diagonal << 32 | cell) of the current window
+    double est_eps;                // candidates: cells within log(threshold) - est_eps of the window's first total (default 0.02)
     int32_t wcap;                // shared-memory columns (power of two)
     // outputs
     int32_t *px, *py, *pw;
@@ -74,7 +87,7 @@ struct Fb2Args {
     unsigned long long *expT;    // EXPECT: per region 25 transition counts (2^-32 fixed point)
     unsigned long long *expE;    // EXPECT: per region 80 emission counts
     double *expLL;               // EXPECT: per region summed total log-probability
-    int32_t dbg;                 // timing experiments only (results are wrong when non-zero)
+    int32_t dbg;                 // PHMM_TUNE builds only: timing experiments (results are wrong when non-zero)
 };
 
 // log(exp(x)+exp(y)), sonLib's piecewise cubic.  Same value, bit for bit, as
@@ -100,8 +113,9 @@ __device__ __forceinline__ double logadd_t(double x, double y, const char *ctab)
 // Shared-memory tables of (emission + transition) sums, one padded row of CS doubles per symbol (pair); the
 // scalar definition adds `from + (eP + tP)`, so the parenthesised sum can be taken once per model.
 //   tM[cX*5+cY][s] = eM[cX][cY] + tr[s -> M]                              s = M, sX, sY, lX, lY
-//   tX[cX][0..4]   = eX[cX] + tr[M->sX], tr[sX->sX], tr[sY->sX], tr[M->lX], tr[lX->lX]
-//   tY[cY][0..4]   = eY[cY] + tr[M->sY], tr[sY->sY], tr[sX->sY], tr[M->lY], tr[lY->lY]
+//   tX[cX][TG_*]   = eX[cX] + tr[M->sX], tr[sX->sX], tr[M->lX], tr[lX->lX], tr[sY->sX]
+//   tY[cY][TG_*]   = eY[cY] + tr[M->sY], tr[sY->sY], tr[M->lY], tr[lY->lY], tr[sX->sY]
+// Rows are TS = 6 doubles apart so that the pairs a cell uses together load as one 16-byte access.
 struct Tabs {
     const double *tM, *tX, *tY;
     const char *ctab;
@@ -140,84 +154,117 @@ __device__ __forceinline__ void st_col(double *p, const double o[NS]) {
     }
 }
 
-// Forward cell from its three predecessor columns: lower = (x-1,y), upper = (x,y-1) on diagonal d-1,
-// middle = (x-1,y-1) on d-2.  Transition order of SURVEY.md A.4.
-template <bool SWITCH, bool GUARD>
-__device__ __forceinline__ void fwd_cell3(const Tabs &t, const double *pl, bool okl, const double *pu, bool oku,
-                                          const double *pm, bool okm, int cX, int cY, double out[NS]) {
-    const double *rM = t.tM + (cX * 5 + cY) * CS, *rX = t.tX + cX * CS, *rY = t.tY + cY * CS;
+// Rows of the (emission + transition) tables, loaded as 16-byte pairs.
+struct GapRow { double s, ss, l, ll, sw; };    // M->short, short->short, M->long, long->long, other short->short (switch)
+template <bool SWITCH>
+__device__ __forceinline__ GapRow ld_gap(const double *r) {
+    const double2 a = *reinterpret_cast<const double2 *>(r + TG_S);
+    const double2 b = *reinterpret_cast<const double2 *>(r + TG_L);
+    GapRow g; g.s = a.x; g.ss = a.y; g.l = b.x; g.ll = b.y; g.sw = SWITCH ? r[TG_SW] : 0.0;
+    return g;
+}
+struct MatRow { double m, sx, sy, lx, ly; };   // s -> M for s = M, sX, sY, lX, lY
+__device__ __forceinline__ MatRow ld_mat(const double *r) {
+    const double2 a = *reinterpret_cast<const double2 *>(r);
+    const double2 b = *reinterpret_cast<const double2 *>(r + 2);
+    MatRow m; m.m = a.x; m.sx = a.y; m.sy = b.x; m.lx = b.y; m.ly = r[4];
+    return m;
+}
+
+// Forward cell from register values.  L = lower (x-1,y), U = upper (x,y-1) on diagonal d-1, C = middle (x-1,y-1)
+// on d-2.  Transition order of SURVEY.md A.4.
+template <bool SWITCH>
+__device__ __forceinline__ void fwd_cell_r(const Tabs &t, int cX, int cY, double LM, double LsX, double LsY, double LlX,
+                                           const ColV &C, double UM, double UsX, double UsY, double UlY, double out[NS]) {
     const char *ctab = t.ctab;
+    const GapRow gx = ld_gap<SWITCH>(t.tX + cX * TS), gy = ld_gap<SWITCH>(t.tY + cY * TS);
+    const MatRow gm = ld_mat(t.tM + (cX * 5 + cY) * TS);
     {
-        const ColV L = ld_col<GUARD>(pl, okl);
-        double a = L.M + rX[0];
-        a = logadd_t(a, L.sX + rX[1], ctab);
-        if (SWITCH) a = logadd_t(a, L.sY + rX[2], ctab);
+        double a = LM + gx.s;
+        a = logadd_t(a, LsX + gx.ss, ctab);
+        if (SWITCH) a = logadd_t(a, LsY + gx.sw, ctab);
         out[S_SX] = a;
-        double b = L.M + rX[3];
-        b = logadd_t(b, L.lX + rX[4], ctab);
+        double b = LM + gx.l;
+        b = logadd_t(b, LlX + gx.ll, ctab);
         out[S_LX] = b;
     }
     {
-        const ColV C = ld_col<GUARD>(pm, okm);
-        double a = C.M + rM[0];
-        a = logadd_t(a, C.sX + rM[1], ctab);
-        a = logadd_t(a, C.sY + rM[2], ctab);
-        a = logadd_t(a, C.lX + rM[3], ctab);
-        a = logadd_t(a, C.lY + rM[4], ctab);
+        double a = C.M + gm.m;
+        a = logadd_t(a, C.sX + gm.sx, ctab);
+        a = logadd_t(a, C.sY + gm.sy, ctab);
+        a = logadd_t(a, C.lX + gm.lx, ctab);
+        a = logadd_t(a, C.lY + gm.ly, ctab);
         out[S_M] = a;
     }
     {
-        const ColV U = ld_col<GUARD>(pu, oku);
-        double a = U.M + rY[0];
-        a = logadd_t(a, U.sY + rY[1], ctab);
-        if (SWITCH) a = logadd_t(a, U.sX + rY[2], ctab);
+        double a = UM + gy.s;
+        a = logadd_t(a, UsY + gy.ss, ctab);
+        if (SWITCH) a = logadd_t(a, UsX + gy.sw, ctab);
         out[S_SY] = a;
-        double b = U.M + rY[3];
-        b = logadd_t(b, U.lY + rY[4], ctab);
+        double b = UM + gy.l;
+        b = logadd_t(b, UlY + gy.ll, ctab);
         out[S_LY] = b;
     }
 }
 
-// Backward cell from its three successor columns: pu = (x, y+1), pl = (x+1, y) on diagonal d+1,
-// pm = (x+1, y+1) on d+2.  cXn = X[x], cYn = Y[y]: the symbols those steps consume.
-template <bool SWITCH, bool GUARD>
-__device__ __forceinline__ void bwd_cell3(const Tabs &t, const double *pl, bool okl, const double *pu, bool oku,
-                                          const double *pm, bool okm, int cXn, int cYn, double out[NS]) {
-    const double *rM = t.tM + (cXn * 5 + cYn) * CS, *rX = t.tX + cXn * CS, *rY = t.tY + cYn * CS;
+// Backward cell from register values: Bm = B_M of (x+1,y+1) on d+2; BsY, BlY of (x,y+1) and BsX, BlX of (x+1,y) on d+1.
+// cXn = X[x], cYn = Y[y]: the symbols those steps consume.
+template <bool SWITCH>
+__device__ __forceinline__ void bwd_cell_r(const Tabs &t, int cXn, int cYn, double Bm, double BsX, double BlX, double BsY,
+                                           double BlY, double out[NS]) {
     const char *ctab = t.ctab;
-    const double Bm = (!GUARD || okm) ? pm[S_M] : PHMM_NEG_INF;
-    const double BsY = (!GUARD || oku) ? pu[S_SY] : PHMM_NEG_INF, BlY = (!GUARD || oku) ? pu[S_LY] : PHMM_NEG_INF;
-    const double BsX = (!GUARD || okl) ? pl[S_SX] : PHMM_NEG_INF, BlX = (!GUARD || okl) ? pl[S_LX] : PHMM_NEG_INF;
+    const GapRow gx = ld_gap<SWITCH>(t.tX + cXn * TS), gy = ld_gap<SWITCH>(t.tY + cYn * TS);
+    const MatRow gm = ld_mat(t.tM + (cXn * 5 + cYn) * TS);
     {
-        double a = Bm + rM[0];
-        a = logadd_t(a, BsY + rY[0], ctab);
-        a = logadd_t(a, BlY + rY[3], ctab);
-        a = logadd_t(a, BsX + rX[0], ctab);
-        a = logadd_t(a, BlX + rX[3], ctab);
+        double a = Bm + gm.m;
+        a = logadd_t(a, BsY + gy.s, ctab);
+        a = logadd_t(a, BlY + gy.l, ctab);
+        a = logadd_t(a, BsX + gx.s, ctab);
+        a = logadd_t(a, BlX + gx.l, ctab);
         out[S_M] = a;
     }
     {
-        double a = Bm + rM[1];
-        if (SWITCH) a = logadd_t(a, BsY + rY[2], ctab);
-        a = logadd_t(a, BsX + rX[1], ctab);
+        double a = Bm + gm.sx;
+        if (SWITCH) a = logadd_t(a, BsY + gy.sw, ctab);
+        a = logadd_t(a, BsX + gx.ss, ctab);
         out[S_SX] = a;
     }
     {
-        double a = Bm + rM[2];
-        a = logadd_t(a, BsY + rY[1], ctab);
-        if (SWITCH) a = logadd_t(a, BsX + rX[2], ctab);
+        double a = Bm + gm.sy;
+        a = logadd_t(a, BsY + gy.ss, ctab);
+        if (SWITCH) a = logadd_t(a, BsX + gx.sw, ctab);
         out[S_SY] = a;
     }
     {
-        double a = Bm + rM[3];
-        a = logadd_t(a, BlX + rX[4], ctab);
+        double a = Bm + gm.lx;
+        a = logadd_t(a, BlX + gx.ll, ctab);
         out[S_LX] = a;
     }
     {
-        double a = Bm + rM[4];
-        a = logadd_t(a, BlY + rY[4], ctab);
+        double a = Bm + gm.ly;
+        a = logadd_t(a, BlY + gy.ll, ctab);
         out[S_LY] = a;
     }
+}
+
+// Forward cell from its three predecessor columns: lower = (x-1,y), upper = (x,y-1) on diagonal d-1,
+// middle = (x-1,y-1) on d-2.
+template <bool SWITCH, bool GUARD>
+__device__ __forceinline__ void fwd_cell3(const Tabs &t, const double *pl, bool okl, const double *pu, bool oku,
+                                          const double *pm, bool okm, int cX, int cY, double out[NS]) {
+    const ColV L = ld_col<GUARD>(pl, okl), C = ld_col<GUARD>(pm, okm), U = ld_col<GUARD>(pu, oku);
+    fwd_cell_r<SWITCH>(t, cX, cY, L.M, L.sX, L.sY, L.lX, C, U.M, U.sX, U.sY, U.lY, out);
+}
+
+// Backward cell from its three successor columns: pu = (x, y+1), pl = (x+1, y) on diagonal d+1,
+// pm = (x+1, y+1) on d+2.
+template <bool SWITCH, bool GUARD>
+__device__ __forceinline__ void bwd_cell3(const Tabs &t, const double *pl, bool okl, const double *pu, bool oku,
+                                          const double *pm, bool okm, int cXn, int cYn, double out[NS]) {
+    const double Bm = (!GUARD || okm) ? pm[S_M] : PHMM_NEG_INF;
+    const double BsY = (!GUARD || oku) ? pu[S_SY] : PHMM_NEG_INF, BlY = (!GUARD || oku) ? pu[S_LY] : PHMM_NEG_INF;
+    const double BsX = (!GUARD || okl) ? pl[S_SX] : PHMM_NEG_INF, BlX = (!GUARD || okl) ? pl[S_LX] : PHMM_NEG_INF;
+    bwd_cell_r<SWITCH>(t, cXn, cYn, Bm, BsX, BlX, BsY, BlY, out);
 }
 
 // left-to-right logAdd fold of n values produced by f(i), starting from -inf (dpDiagonal_dotProduct order)
@@ -320,13 +367,13 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
     const int wcap = a.wcap, cmask = wcap - 1;
     double *const sbuf = reinterpret_cast<double *>(smem_raw);                  // [2][wcap][CS]
     double *const sct = sbuf + 2 * CS * wcap;                                    // 4 rows x (c3 c2 c1 c0)
-    double *const stM = sct + 16, *const stX = stM + 25 * CS, *const stY = stX + 5 * CS;
+    double *const stM = sct + 16, *const stX = stM + 25 * TS, *const stY = stX + 5 * TS;
     DiagRec *const srec = reinterpret_cast<DiagRec *>(sct + FB2_TAB);            // [2][FB2_RQ]
     __shared__ int s_region;
     __shared__ int s_npairs;
     __shared__ double s_est;                           // total of the window's first posterior diagonal
     __shared__ int s_ncand, s_estok;
-    constexpr double EST_EPS = 0.02;                   // how far a window's totals may lie from s_est (verified per window)
+    const double EST_EPS = a.est_eps;                  // how far a window's totals may lie from s_est (verified per window)
     __shared__ EmisTables etab;                        // EXPECT
     __shared__ unsigned long long sT[EXPECT ? 25 : 1];
     __shared__ unsigned long long sE[EXPECT ? 80 : 1];
@@ -342,14 +389,15 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
         sct[8] = -0.004605031767994; sct[9] = 0.063427417320019; sct[10] = 0.695956496475118; sct[11] = 0.514272634594009;
         sct[12] = -0.000458661602210; sct[13] = 0.009695946122598; sct[14] = 0.930734667215156; sct[15] = 0.168037164329057;
     }
-    for (int i = tid; i < 25 * CS; i += NTA) {
-        const int r = i / CS, s = i - r * CS;
+    for (int i = tid; i < 25 * TS; i += NTA) {
+        const int r = i / TS, s = i - r * TS;
         stM[i] = s < NS ? a.m.eM[r] + a.m.tr[s * 5 + S_M] : 0.0;
     }
-    if (tid < 5 * CS) {
-        const int c = tid / CS, s = tid - c * CS;
-        const int fx[5] = {S_M * 5 + S_SX, S_SX * 5 + S_SX, S_SY * 5 + S_SX, S_M * 5 + S_LX, S_LX * 5 + S_LX};
-        const int fy[5] = {S_M * 5 + S_SY, S_SY * 5 + S_SY, S_SX * 5 + S_SY, S_M * 5 + S_LY, S_LY * 5 + S_LY};
+    if (tid < 5 * TS) {
+        const int c = tid / TS, s = tid - c * TS;
+        // slots TG_S, TG_SS, TG_L, TG_LL, TG_SW
+        const int fx[5] = {S_M * 5 + S_SX, S_SX * 5 + S_SX, S_M * 5 + S_LX, S_LX * 5 + S_LX, S_SY * 5 + S_SX};
+        const int fy[5] = {S_M * 5 + S_SY, S_SY * 5 + S_SY, S_M * 5 + S_LY, S_LY * 5 + S_LY, S_SX * 5 + S_SY};
         stX[tid] = s < NS ? a.m.eX[c] + a.m.tr[fx[s < NS ? s : 0]] : 0.0;
         stY[tid] = s < NS ? a.m.eY[c] + a.m.tr[fy[s < NS ? s : 0]] : 0.0;
     }
@@ -442,16 +490,16 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                 {
                     const bool tot = (rc.pad & REC_TOT) != 0;
                     double *const rg = ring + rc.off;
-                    if (a.dbg & 32) {
+                    if (FB2_DBG(32)) {
                     } else if (fast) {
                         // the three diagonals are in shared memory and every out-of-band neighbour reads -inf
                         double *const b0 = sbuf + par * wcap * CS;
                         const double *const b1 = sbuf + (par ^ 1) * wcap * CS;
                         const int dl = par ? -1 : 0;                  // lower is in column c-1 (odd d) or c (even d); upper one further
-                        for (int i = (tid - clo) & (NC - 1); i < w; i += NC) {
+                        for (int i = tid; i < w; i += NC) {
                             const int x = xlo + i, y = d - x;
                             int cX, cY;
-                            if (a.dbg & 1) { cX = x & 3; cY = y & 3; }
+                            if (FB2_DBG(1)) { cX = x & 3; cY = y & 3; }
                             else { cX = x >= 1 ? X[x - 1] : 4; cY = y >= 1 ? Y[y - 1] : 4; }
                             const int c = clo + i;
                             double *const p0 = b0 + (c & cmask) * CS;                      // own column == middle's
@@ -460,7 +508,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                             double o[NS];
                             fwd_cell3<SWITCH, false>(tabs, pl, true, pu, true, p0, true, cX, cY, o);
                             st_col<true>(p0, o);
-                            if (!(a.dbg & 2)) {
+                            if (!FB2_DBG(2)) {
                             rg[i] = o[S_M];
                             if (tot || EXPECT) {
 #pragma unroll
@@ -508,7 +556,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                     }
                     __syncthreads();
                 }
-                if (d == P && (a.dbg & 16)) {
+                if (d == P && FB2_DBG(16)) {
                     traced_to = d - (d == nd ? 0 : tbd);
                     tk++;
                     P = tk < ntb ? tb[tk] : nd + 1;
@@ -549,12 +597,12 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                             {
                                 double *const rg = ring + rb.off;
                                 const bool dots = (rb.pad & REC_TOT) != 0 && dd <= traced_from;
-                                if (a.dbg & 256) {
+                                if (FB2_DBG(256)) {
                                 } else if (bfast) {
                                     double *const b0 = sbuf + bpar * wcap * CS;
                                     const double *const b1 = sbuf + (bpar ^ 1) * wcap * CS;
                                     const int du = bpar ? -1 : 0;     // (x, y+1) is in column c-1 (odd dd) or c (even dd); (x+1, y) one further
-                                    for (int i = (tid - bclo) & (NC - 1); i < rb.w; i += NC) {
+                                    for (int i = tid; i < rb.w; i += NC) {
                                         const int x = rb.xlo + i, y = dd - x;
                                         const int cXn = x < lx ? X[x] : 4;
                                         const int cYn = y < ly ? Y[y] : 4;
@@ -662,7 +710,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                     }
                     // phase 2: total probabilities, one thread per total diagonal
                     const int nk = traced_from > traced_to ? (traced_from - traced_to - 1) / TOTAL_EVERY + 1 : 0;
-                    for (int k = tid; k < ((a.dbg & 64) ? 0 : nk); k += NTA) {
+                    for (int k = tid; k < (FB2_DBG(64) ? 0 : nk); k += NTA) {
                         const int dd = traced_from - TOTAL_EVERY * k;
                         const DiagRec r0 = rec[dd];
                         const double *cd = ring + r0.off + DOT * r0.w;
@@ -731,7 +779,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                         }
                     };
                     const int ncand = s_ncand;
-                    if (!EXPECT && s_estok && ncand <= a.ccap && !(a.dbg & (128 | 512)) && traced_from > traced_to) {
+                    if (!EXPECT && s_estok && ncand <= a.ccap && !FB2_DBG(128 | 512) && traced_from > traced_to) {
                         {
                             const DiagRec r0 = rec[traced_from];
                             const double *sm = ring + r0.off;
@@ -744,7 +792,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                             emit(dd, i, r0.xlo, ring[r0.off + i], totals[(traced_from - dd) / TOTAL_EVERY]);
                         }
                     } else
-                    for (int dd = EXPECT ? traced_to : traced_from - (tid >> 5); dd > ((a.dbg & 128) ? traced_from : traced_to); dd -= NW) {
+                    for (int dd = EXPECT ? traced_to : traced_from - (tid >> 5); dd > (FB2_DBG(128) ? traced_from : traced_to); dd -= NW) {
                         const DiagRec r0 = rec[dd];
                         const double total = totals[(traced_from - dd) / TOTAL_EVERY];
                         const double *sm = ring + r0.off;

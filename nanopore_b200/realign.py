@@ -23,12 +23,19 @@ import os
 
 import numpy as np
 
-from . import capi
+from . import capi, io_native
 from .batch import Batch, encode, pack_ops, unpack_ops
 from .bioio import (PairwiseAlignment, cigarReadFromString, fastaRead, fastqRead, logger, reverseComplement)
 from .engine import Realigner
 from .hmm import Hmm
 from .sam import AlignedRead, Samfile
+
+# File-level steps (chain, pack, fan-in) go through libphmm_io.so (C++, threaded) when it is built; the Python
+# functions below restate the same reference code, serve custom chain functions, and are what the tests compare the
+# native path with, byte for byte.  NANOPORE_B200_PYTHON_IO=1 forces them.
+def useNativeIo():
+    return io_native.available() and os.environ.get("NANOPORE_B200_PYTHON_IO", "0") != "1"
+
 
 REALIGN_DIAGONAL_EXPANSION = 10          # utils.py:587
 REALIGN_SPLIT_MATRIX_BIGGER_THAN = 3000  # utils.py:587
@@ -196,6 +203,16 @@ def mergeChainedAlignedReads(chainedAlignedReads, refSequence, readSequence):
 
 def chainSamFile(samFile, outputSamFile, readFastqFile, referenceFastaFile, chainFn=chainFn):
     """Each (read, reference) pair is covered by a single maximal global alignment (utils.py:441-469)."""
+    if chainFn is globals()["chainFn"] and useNativeIo():
+        io = io_native.NativeIo()
+        try:
+            io.load_reference(referenceFastaFile)
+            io.load_reads(readFastqFile)
+            io.chain_sam(samFile)
+            io.write_sam(outputSamFile)
+        finally:
+            io.close()
+        return
     sam = Samfile(samFile, "r")
     refSequences = getFastaDictionary(referenceFastaFile)
     readSequences = getFastqDictionary(readFastqFile)
@@ -314,6 +331,24 @@ def realignSamFileTargetFn(target, samFile, outputSamFile, readFastqFile, refere
 def realignSamFile2TargetFn(target, samFile, outputSamFile, readFastqFile, referenceFastaFile, hmmFile, gapGamma, matchGamma):
     """Realigns every mapped record of samFile in one batched call and hands the ops to the fan-in
     (utils.py:557-574; the per-read child jobs and their temp cigar files are gone)."""
+    if useNativeIo():
+        io = io_native.NativeIo()
+        try:
+            io.load_reference(referenceFastaFile)
+            io.load_sam(samFile)
+            batch = io.batch()
+            realigner = makeRealigner(hmm=loadHmmOrNone(hmmFile))
+            try:
+                realigner.set_reference(batch.ref)
+                ops, off, _ = realigner.realign(batch, realignParams(gapGamma, matchGamma))
+            finally:
+                realigner.close()
+            assert len(off) == batch.n + 1                 # exactly one cigar per read (utils.py:588-589)
+            target.logToMaster("Realigned %d reads (%d DP cells) from %s" % (batch.n, getattr(realigner, "cells", 0), samFile))
+            io.write_realigned_sam(outputSamFile, ops, off)   # the fan-in of realignSamFile3TargetFn (utils.py:591-609)
+        finally:
+            io.close()
+        return
     refSequences = getFastaDictionary(referenceFastaFile)
     sam = Samfile(samFile, "r")
     records = list(samIterator(sam))

@@ -1,9 +1,16 @@
 """Kernel-only timing of the realignment path under library options (GPU box).
-usage: python scripts/tune.py READS "opt=val,opt=val" ["opt=val" ...]"""
+usage: python scripts/tune.py READS "opt=val,opt=val" ["opt=val" ...]
+
+Loads build/libphmm_tune.so (built HERE with -DPHMM_TUNE by `python -c "from nanopore_b200 import build; build.build_tune()"`,
+it travels with the snapshot) when it exists, so that the timing_experiment switches are available; the shipped
+library rejects them."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from nanopore_b200 import capi, synth
+_tune = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "libphmm_tune.so")
+if os.path.exists(_tune) and os.environ.get("SHIPPED_LIB") != "1":
+    capi.LIB_PATH = _tune
 
 n = int(sys.argv[1])
 band = int(os.environ.get("BAND", "50"))

@@ -73,3 +73,23 @@ def test_loader_rejects_wrong_sizes(tmp_path):
     p.write_text("1 0.5 0.5 0.0\n0.1 0.2\n")
     with pytest.raises(RuntimeError):
         H.Hmm.loadHmm(str(p))
+
+
+@pytest.mark.parametrize("name,rate", [("blasr_hmm_20.txt", "0.2"), ("blasr_hmm_40.txt", "0.4")])
+def test_modify_hmm_command_line(golden_dir, tmp_path, name, rate):
+    """scripts/modifyHmm.py IN GC RATE OUT (reference scripts/modifyHmm.py:7-30) regenerates the reference's files."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "out.hmm"
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "modifyHmm.py"),
+                        os.path.join(golden_dir, "blasr_hmm_0.txt"), "0.5", rate, str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Got GC content 0.5" in r.stdout and "For state, ref frequencies" in r.stdout
+    got, want = H.Hmm.loadHmm(str(out)), _load(golden_dir, name)
+    assert got.transitions == want.transitions and got.likelihood == want.likelihood
+    assert np.abs(np.array(got.emissions) - np.array(want.emissions)).max() < 1e-12
+    # wrong argument count: usage, non-zero exit
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "modifyHmm.py")], capture_output=True, text=True)
+    assert r.returncode == 2
