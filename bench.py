@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = 4 x cores, about 15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-files", action="store_true", help="skip the SAM-in / SAM-out leg (e2e_files)")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="library option (phmm_set_option) for kernel experiments, e.g. register_path=0; recorded in config")
     return ap.parse_args()
@@ -71,6 +72,17 @@ def traffic_per_cell():
         return (float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])) / float(t["cells"])
     except Exception:
         return None
+
+
+def thread_inst_per_cell():
+    """Thread-instructions per DP cell of k_fb2 from the same committed capture (None if absent)."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["thread_inst_per_cell"])
+    except Exception:
+        return None
+
+
+ISSUE_PEAK = 148 * 4 * 32 * 1.965e9        # thread-instructions/s: 148 SMs x 4 schedulers x 32 lanes x 1965 MHz
 
 
 def peaks():
@@ -157,6 +169,72 @@ def cpu_realign_sample(b, idx, band, threads):
         res = list(ex.map(one, idx))
     dt = time.perf_counter() - t0
     return dt, int(sum(c for c, _ in res)), [o for _, o in res]
+
+
+def write_experiment(b, dirname):
+    """The batch as the files a mapper leaves behind (reference FASTA, read FASTQ, SAM of one local hit per read): the
+    input of AbstractMapper.realignSamFile.  Reverse-strand reads sit reverse-complemented in the FASTQ, as reads do."""
+    from nanopore_b200 import synth
+    from nanopore_b200.bioio import reverseComplement
+    os.makedirs(dirname, exist_ok=True)
+    fa, fq, sam = (os.path.join(dirname, n) for n in ("reference.fa", "reads.fq", "mapping.sam"))
+    ref = synth.decode(b.ref)
+    with open(fa, "w") as fh:
+        fh.write(">ref synthetic\n")
+        fh.write("\n".join(ref[i:i + 100] for i in range(0, len(ref), 100)) + "\n")
+    letters = np.array(list("MID"))
+    with open(fq, "w") as fqh, open(sam, "w") as sh:
+        sh.write("@HD\tVN:1.0\tSO:unsorted\n@SQ\tSN:ref\tLN:%d\n" % len(ref))
+        for i in range(b.n):
+            seq = synth.decode(b.read(i))
+            o = b.ops(i)
+            code, ln = (o & 3).astype(np.int64), (o >> 2).astype(np.int64)
+            lead = int(ln[0]) if code[0] == 2 else 0                     # chained-global guide: D(window start) local D(tail)
+            a = 1 if code[0] == 2 else 0
+            z = len(o) - 1 if code[-1] == 2 and len(o) > a + 1 else len(o)
+            cig = "".join(np.char.add(ln[a:z].astype("U12"), letters[code[a:z]]).tolist())
+            rev = bool(b.reverse[i]) if b.reverse is not None else False
+            name = b.names[i] if b.names else "read_%d" % i
+            fqh.write("@%s\n%s\n+\n%s\n" % (name, reverseComplement(seq) if rev else seq, "2" * len(seq)))
+            sh.write("\t".join([name, "16" if rev else "0", "ref", str(int(b.ref_start[i]) + lead + 1), "30", cig, "*", "0", "0", seq, "*"]) + "\n")
+    return fa, fq, sam
+
+
+def realign_files(sam, fq, fa, out_sam):
+    """What a `*Realign*` mapper does after mapping (reference nanopore/mappers/abstractMapper.py:25-39): chain, realign,
+    rewrite the SAM -- through the plugin class and the in-process Target runner."""
+    import shutil
+    from nanopore_b200.mappers.abstractMapper import AbstractMapper
+    from nanopore_b200.target import Stack
+
+    class Realign(AbstractMapper):
+        def run(self):
+            self.realignSamFile(gapGamma=0.5, matchGamma=0.0)
+
+    shutil.copyfile(sam, out_sam)
+    failed = Stack(Realign(fq, "2D", fa, out_sam)).startJobTree(None)
+    if failed:
+        raise RuntimeError("%d job(s) failed" % failed)
+
+
+def per_read_process_overhead(b, n=16):
+    """What the reference pays per read besides the DP (utils.py:582-587): the whole reference and the read written as
+    FASTA, one `sh -c "echo cigar | ..."` process, the cigar file read back.  `cat` stands in for cactus_realign."""
+    import subprocess
+    import tempfile
+    from nanopore_b200 import synth
+    ref = synth.decode(b.ref)
+    t0 = time.perf_counter()
+    with tempfile.TemporaryDirectory() as d:
+        for i in range(min(n, b.n)):
+            with open(os.path.join(d, "ref.fa"), "w") as fh:
+                fh.write(">ref\n%s\n" % ref)
+            with open(os.path.join(d, "read.fa"), "w") as fh:
+                fh.write(">read\n%s\n" % synth.decode(b.read(i)))
+            cig = "cigar: read 0 %d + ref 0 %d + 1 M %d" % (len(b.read(i)), len(ref), len(b.read(i)))
+            subprocess.check_call("echo '%s' | cat > %s" % (cig, os.path.join(d, "out.cig")), shell=True)
+            open(os.path.join(d, "out.cig")).read()
+    return 1e3 * (time.perf_counter() - t0) / max(1, min(n, b.n))
 
 
 def run_reference(args, rank, world):
@@ -270,6 +348,7 @@ def main():
     if not args.no_e2e:
         pin = [torch.from_numpy(a).pin_memory().numpy() for a in (b.reads, b.read_off, b.ref_start, b.ref_end, b.in_ops, b.in_off)]
         ctx.realign_batch(*pin, params)                           # warm-up (allocations)
+        launches_e2e = 0
         barrier()
         t0 = time.perf_counter()
         e0.record()
@@ -283,6 +362,80 @@ def main():
         h2d += int(est["h2d_bytes"]) - int(b.reads.nbytes)        # + planned regions / anchor runs the library uploads
         d2h = int(est["d2h_bytes"])
         assert np.array_equal(ops2, ops) and np.array_equal(off2, off)
+
+    # ---------------- end to end on N GPUs: ONE batch on rank 0 through the rank-sharded realigner ----------------
+    sharded = None
+    if not args.no_e2e and world > 1:
+        from nanopore_b200 import parallel
+        from nanopore_b200.batch import Batch
+        ctx.close()                                                  # the realigners of nanopore_b200.parallel own the GPUs now
+        fields = ("reads", "read_off", "ref_start", "ref_end", "in_ops", "in_off")
+        if rank == 0:
+            parts = [[getattr(b, f) for f in fields]] + [parallel._unpack(parallel._recv_blob(r)) for r in range(1, world)]
+            cat = lambda k: np.concatenate([p[k] for p in parts])
+            offs = lambda k, d: np.concatenate([[0]] + [p[k][1:] + sum(int(q[k][-1]) for q in parts[:j]) for j, p in enumerate(parts)]).astype(np.int64)
+            big = Batch(b.ref, cat(0), offs(1, 0), cat(2), cat(3), cat(4), offs(5, 0))
+            sr = parallel.ShardedRealigner(None)
+            sr.set_reference(b.ref)
+            sr.realign(big, params)                                  # warm-up (contexts, allocations)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(max(1, args.steps)):
+                sr._sent = None                                      # a new batch every step: the scatter is inside the timed region
+                ops_s, off_s, _ = sr.realign(big, params)
+            e1.record()
+            torch.cuda.synchronize()
+            sh_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / max(1, args.steps)
+            assert np.array_equal(ops_s[:len(ops)], ops) and np.array_equal(off_s[:b.n + 1], off)     # rank 0's own reads: same CIGARs
+            sharded = {"value": big.n / (sh_ms * 1e-3), "unit": "reads/s", "ms_per_step": sh_ms, "reads_per_step": int(big.n),
+                       "h2d_bytes_per_step": int(sum(getattr(big, f).nbytes for f in fields)), "d2h_bytes_per_step": int(ops_s.nbytes + off_s.nbytes),
+                       "cells": int(sr.cells),
+                       "path": "nanopore_b200.parallel.ShardedRealigner: one batch in rank 0's host memory, shards balanced on "
+                               "estimated DP cells and sent point to point, CIGAR ops returned to rank 0 in input order"}
+            sr.close()
+            parallel.shutdown()
+        else:
+            parallel._send_blob(parallel._pack([getattr(b, f) for f in fields]), 0)
+            parallel.worker_loop()
+
+    # ---------------- end to end from files (1 GPU): SAM + FASTQ + FASTA in, realigned SAM out ----------------
+    files = None
+    if not args.no_e2e and world == 1 and not args.no_files:
+        import shutil
+        import tempfile
+        ctx.close()
+        base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        d = tempfile.mkdtemp(prefix="phmm_bench_", dir=base)
+        try:
+            fa, fq, sam = write_experiment(b, d)
+            out_sam = os.path.join(d, "realigned.sam")
+            realign_files(sam, fq, fa, out_sam)                      # warm-up
+            nrun = max(1, min(args.steps, 2))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(nrun):
+                realign_files(sam, fq, fa, out_sam)
+            torch.cuda.synchronize()
+            f_ms = 1e3 * (time.perf_counter() - t0) / nrun
+            # same CIGARs as the packed path (the chained file is sorted by name: compare by name)
+            got = {}
+            for ln in open(out_sam):
+                if not ln.startswith("@"):
+                    f = ln.split("\t", 6)
+                    got[f[0]] = f[5]
+            assert len(got) == b.n
+            letters = np.array(list("MID"))
+            for i in range(0, b.n, max(1, b.n // 64)):
+                o = ops[off[i]:off[i + 1]]
+                want = "".join(np.char.add((o >> 2).astype("U12"), letters[(o & 3).astype(np.int64)]).tolist())
+                assert got[b.names[i]] == want, "CIGAR of %s from files differs from the packed path" % b.names[i]
+            files = {"value": b.n / (f_ms * 1e-3), "unit": "reads/s", "ms_per_step": f_ms,
+                     "bytes_in": int(sum(os.path.getsize(x) for x in (fa, fq, sam))), "bytes_out": int(os.path.getsize(out_sam)),
+                     "path": "AbstractMapper.realignSamFile: native chain (libphmm_io.so) -> temp.sam -> native load + pack -> "
+                             "phmm_realign_batch -> native SAM emit"}
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
 
     # ---------------- reduce over ranks: max time, sums of work ----------------
     vec = torch.tensor([ms, fb_ms, dec_ms, e2e_ms or 0.0], dtype=torch.float64, device=dev)
@@ -307,7 +460,12 @@ def main():
                              "traffic_source": TRAFFIC_SRC,
                              "algorithmic_bytes_per_launch": BYTES_PER_CELL * cells_rank, "cells_per_launch": cells_rank,
                              "kernel_ms": fb_ms / args.steps, "kernel_share_of_step": fb_ms / ms,
-                             "frac_of_datasheet_8TBs": achieved / 8000.0},
+                             "frac_of_datasheet_8TBs": achieved / 8000.0,
+                             # the bound the counters show (DRAM is ~5 % busy): instruction issue.  cells/s x thread-instructions
+                             # per cell (committed ncu capture) / what 148 SMs can issue
+                             "issue_frac": (cells_rank / (fb_ms / args.steps * 1e-3)) * thread_inst_per_cell() / ISSUE_PEAK
+                             if thread_inst_per_cell() else None,
+                             "thread_inst_per_cell": thread_inst_per_cell()},
                 "clocks": clocks, "gpu_launches": launches,
                 "cells_per_read": cells_total / reads_total, "pairs": st["pairs"], "regions": st["n_regions"],
                 "resident_regions": st["n_slots"], "decode_ms": dec_ms / args.steps}
@@ -315,7 +473,14 @@ def main():
             line["config"]["library_options"] = list(args.opt)
         if e2e_ms is not None:
             line["e2e"] = {"value": reads_total / (e2e_max * 1e-3), "unit": "reads/s", "h2d_bytes_per_step": h2d,
-                           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_max}
+                           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_max,
+                           "path": "phmm_realign_batch from pinned host buffers on every rank (its own shard)"}
+        if sharded is not None:
+            # N GPUs: the product path.  e2e = one batch on rank 0 through the sharded realigner; the per-rank call is kept beside it
+            line["e2e_per_rank_call"] = line.get("e2e")
+            line["e2e"] = sharded
+        if files is not None:
+            line["e2e_files"] = files
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n = args.cpu_sample or 4 * cores
@@ -327,8 +492,14 @@ def main():
                                     "sample": "first %d reads of the step's batch, one read per task on %d threads (%.1f s); "
                                               "CIGARs compared with the GPU output" % (len(idx), cores, dt),
                                     "cells_per_s": ccells / dt}
+            # the reference's own default: 4 workers (Makefile:1 maxThreads=4), and what it pays per read besides the DP
+            i4 = list(range(min(8, b.n)))
+            dt4, _, _ = cpu_realign_sample(b, i4, args.band, 4)
+            line["cpu_baseline"]["four_workers"] = {"value": len(i4) / dt4, "unit": "reads/s", "cores": 4,
+                                                    "sample": "%d reads on 4 threads (reference Makefile:1 maxThreads=4)" % len(i4)}
+            line["cpu_baseline"]["per_read_process_overhead_ms"] = per_read_process_overhead(b)
         print(json.dumps(line), flush=True)
-    ctx.close()
+    ctx.close()                                                      # idempotent
     if world > 1:
         dist.destroy_process_group()
     return 0

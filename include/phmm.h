@@ -144,6 +144,18 @@ int phmm_expectations_batch(phmm_ctx *ctx, int64_t n_reads,
                             const uint32_t *in_cigar_ops, const int64_t *in_cigar_off,
                             const phmm_params *params, double out_stats[106]);
 
+/* Resident E-step for EM: prepare the batch ONCE (host planning, upload, band geometry, diagonal records), then
+ * per iteration phmm_set_model + phmm_expectations_run_fixed.  phmm_set_model keeps a prepared batch (the plan does
+ * not depend on the model).  Replaces the reference's schedule of 3 trials x 100 iterations, each of which
+ * re-launches cactus_realign --outputExpectations over the same alignments (utils.py:509-528).  A sub-problem with
+ * zero probability under the model (non-finite log-likelihood) is reported as PHMM_E_ARG naming the read. */
+int phmm_expectations_prepare(phmm_ctx *ctx, int64_t n_reads,
+                              const uint8_t *read_bases, const int64_t *read_off,
+                              const int64_t *ref_start, const int64_t *ref_end,
+                              const uint32_t *in_cigar_ops, const int64_t *in_cigar_off,
+                              const phmm_params *params);
+int phmm_expectations_run_fixed(phmm_ctx *ctx, int64_t out_hi[106], int64_t out_lo[106]);
+
 /* Same E-step as exact integers, for deterministic reduction over calls, ranks and GPUs (the reference sums
  * expectation files in double, utils.py:528 via cactus_expectationMaximisation; integer sums make the trained
  * HMM independent of how the reads were sharded).  Value k = out_hi[k] + out_lo[k] / 2^32 for k < 105

@@ -79,6 +79,22 @@ int phmm_io_write_sam(phmm_io *io, const char *out_path);
  * replaced by ops[off[i] .. off[i+1]) (the arrays phmm_realign_batch returned for the batch view). */
 int phmm_io_write_realigned_sam(phmm_io *io, const char *out_path, const uint32_t *ops, const int64_t *off, int64_t n);
 
+/* Host helpers of the rank-sharded path (no handle; threads <= 0 = all host cores).
+ *
+ * phmm_io_estimate_cells: estimated DP cells of every read from its guide cigar alone -- anchor runs (matches longer
+ * than 2 * anchor_trim) cost 2 n (band + 1), the block between two anchor runs its band rectangle
+ * (dx + band + 1)(dy + band + 1), a block above split_side^2 only its two corner rectangles.  The
+ * cost that balances shards across GPUs and bounds one library call; the exact count comes back from
+ * phmm_batch_get_stats.  The reference balances nothing: one jobTree job per read (utils.py:565-570).
+ *
+ * phmm_io_gather_ranges: the ragged rows idx[0..n_idx) of (data, off) copied to out at out_off -- how a shard's reads
+ * and guide cigars are cut out of the batch. */
+int phmm_io_estimate_cells(int64_t n, const uint32_t *ops, const int64_t *ops_off, const int64_t *read_off,
+                           const int64_t *ref_start, const int64_t *ref_end, int band, int anchor_trim,
+                           int64_t split_side, int threads, int64_t *out_cells);
+int phmm_io_gather_ranges(const void *data, const int64_t *off, const int64_t *idx, int64_t n_idx, int elem_size,
+                          int threads, void *out, const int64_t *out_off);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,7 @@ EXPORTS = [
     "phmm_last_error", "phmm_set_stream", "phmm_set_model", "phmm_set_reference", "phmm_realign_batch",
     "phmm_expectations_batch", "phmm_expectations_batch_fixed", "phmm_batch_prepare", "phmm_batch_run", "phmm_batch_fetch",
     "phmm_batch_get_stats", "phmm_set_memory_budget", "phmm_set_option", "phmm_free", "phmm_free_posteriors",
+    "phmm_expectations_prepare", "phmm_expectations_run_fixed",
 ]
 
 
@@ -83,6 +84,8 @@ def load_library():
                                                 C.POINTER(Posteriors)]
     L.phmm_expectations_batch.argtypes = batch_in + [vp]
     L.phmm_expectations_batch_fixed.argtypes = batch_in + [vp, vp]
+    L.phmm_expectations_prepare.argtypes = batch_in
+    L.phmm_expectations_run_fixed.argtypes = [vp, vp, vp]
     L.phmm_batch_prepare.argtypes = batch_in
     L.phmm_batch_run.argtypes = [vp]
     L.phmm_batch_fetch.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_int64)),
@@ -243,4 +246,16 @@ class PhmmContext:
         lo = np.zeros(106, dtype=np.int64)
         self._check(self._lib.phmm_expectations_batch_fixed(self._h, n, *[_ptr(x) for x in a], C.byref(params),
                                                             _ptr(hi), _ptr(lo)))
+        return hi, lo
+
+    def expectations_prepare(self, reads, read_off, ref_start, ref_end, in_ops, in_off, params):
+        """Resident E-step: plans and uploads the batch once; expectations_run_fixed() then runs per EM iteration
+        (set_model in between keeps the plan)."""
+        n, a = self._batch_arrays(reads, read_off, ref_start, ref_end, in_ops, in_off)
+        self._check(self._lib.phmm_expectations_prepare(self._h, n, *[_ptr(x) for x in a], C.byref(params)))
+
+    def expectations_run_fixed(self):
+        hi = np.zeros(106, dtype=np.int64)
+        lo = np.zeros(106, dtype=np.int64)
+        self._check(self._lib.phmm_expectations_run_fixed(self._h, _ptr(hi), _ptr(lo)))
         return hi, lo

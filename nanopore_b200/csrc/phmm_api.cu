@@ -465,6 +465,8 @@ int do_prepare(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const 
         const int64_t lX = ref_end[i] - ref_start[i];
         if (lY < 0 || lX < 0 || ref_start[i] < 0 || ref_end[i] > ctx->ref_len)
             return fail(ctx, PHMM_E_ARG, "read " + std::to_string(i) + ": coordinates outside the reference or negative length");
+        if (lX > 0x3fffffff || lY > 0x3fffffff)      // region origins and posterior positions are 32-bit
+            return fail(ctx, PHMM_E_ARG, "read " + std::to_string(i) + ": window or read longer than 2^30 - 1 bases");
         b.read_first_region[i] = (int64_t)b.regions.size();
         b.read_lx[i] = lX; b.read_ly[i] = lY;
         rc = plan_read(ctx, i, in_ops + in_off[i], in_off[i + 1] - in_off[i], lX, lY, ref_start[i], read_off[i], *params, b.regions, b.runs);
@@ -701,7 +703,7 @@ int phmm_set_model(phmm_ctx *ctx, const double *trans, const double *emis, int m
     if ((trans == nullptr) != (emis == nullptr)) return fail(ctx, PHMM_E_ARG, "trans and emis must both be given or both be NULL");
     if (model_type != 0 && model_type != 1) return fail(ctx, PHMM_E_ARG, "model_type must be 0 or 1");
     build_model(ctx->model, trans, emis);
-    ctx->b.prepared = false; ctx->b.ran = false;
+    ctx->b.ran = false;                     // the plan of a prepared batch (regions, geometry, records) does not depend on the model
     return PHMM_OK;
 }
 
@@ -953,13 +955,8 @@ int phmm_realign_batch(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases
 // E-step of one batch as exact integers: out_hi[k] + out_lo[k] / 2^32 for the 105 expectations (the kernels
 // accumulate in 2^-32 fixed point), out_hi[105] + out_lo[105] / 2^20 for the summed log-likelihood (per-region
 // values rounded to 2^-20).  Integer sums are independent of the order of regions, reads, calls and ranks.
-static int expectations_fixed(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const int64_t *read_off,
-                              const int64_t *ref_start, const int64_t *ref_end, const uint32_t *in_cigar_ops,
-                              const int64_t *in_cigar_off, const phmm_params *params, int64_t out_hi[106], int64_t out_lo[106]) {
-    int rc = do_prepare(ctx, n_reads, read_bases, read_off, ref_start, ref_end, in_cigar_ops, in_cigar_off, params, true);
-    if (rc) return rc;
-    rc = do_run(ctx);
-    if (rc) return rc;
+// Sums the per-region statistics of the E-step that just ran.
+static int expectations_reduce(phmm_ctx *ctx, int64_t out_hi[106], int64_t out_lo[106]) {
     BatchState &b = ctx->b;
     const int64_t nreg = (int64_t)b.regions.size();
     std::vector<unsigned long long> T(nreg * 25), E(nreg * 80);
@@ -973,6 +970,11 @@ static int expectations_fixed(phmm_ctx *ctx, int64_t n_reads, const uint8_t *rea
     __int128 acc[106];
     for (int k = 0; k < 106; k++) acc[k] = 0;
     for (int64_t g = 0; g < nreg; g++) {
+        // a sub-problem no path of the model can explain (zero transitions in a sparse or random-start HMM) has no
+        // finite likelihood and its expectations are meaningless: report it instead of summing garbage
+        if (!std::isfinite(LL[g]))
+            return fail(ctx, PHMM_E_ARG, "read " + std::to_string(b.regions[g].read) + " has zero probability under the model (region " +
+                                             std::to_string(g) + ": log-likelihood is not finite)");
         for (int k = 0; k < 25; k++) acc[k] += (__int128)(int64_t)T[g * 25 + k];
         for (int k = 0; k < 80; k++) acc[25 + k] += (__int128)(int64_t)E[g * 80 + k];
         acc[105] += (__int128)llrint(LL[g] * 1048576.0);
@@ -983,6 +985,39 @@ static int expectations_fixed(phmm_ctx *ctx, int64_t n_reads, const uint8_t *rea
         out_lo[k] = (int64_t)(acc[k] - ((__int128)out_hi[k] << bits));         // in [0, 2^bits)
     }
     return PHMM_OK;
+}
+
+// E-step of one batch as exact integers: out_hi[k] + out_lo[k] / 2^32 for the 105 expectations (the kernels
+// accumulate in 2^-32 fixed point), out_hi[105] + out_lo[105] / 2^20 for the summed log-likelihood (per-region
+// values rounded to 2^-20).  Integer sums are independent of the order of regions, reads, calls and ranks.
+static int expectations_fixed(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const int64_t *read_off,
+                              const int64_t *ref_start, const int64_t *ref_end, const uint32_t *in_cigar_ops,
+                              const int64_t *in_cigar_off, const phmm_params *params, int64_t out_hi[106], int64_t out_lo[106]) {
+    int rc = do_prepare(ctx, n_reads, read_bases, read_off, ref_start, ref_end, in_cigar_ops, in_cigar_off, params, true);
+    if (rc) return rc;
+    rc = do_run(ctx);
+    if (rc) return rc;
+    return expectations_reduce(ctx, out_hi, out_lo);
+}
+
+int phmm_expectations_prepare(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const int64_t *read_off,
+                              const int64_t *ref_start, const int64_t *ref_end, const uint32_t *in_cigar_ops,
+                              const int64_t *in_cigar_off, const phmm_params *params) {
+    if (!ctx) return PHMM_E_ARG;
+    try {
+        return do_prepare(ctx, n_reads, read_bases, read_off, ref_start, ref_end, in_cigar_ops, in_cigar_off, params, true);
+    } catch (const std::exception &ex) { return fail(ctx, PHMM_E_NOMEM, ex.what()); }
+}
+
+int phmm_expectations_run_fixed(phmm_ctx *ctx, int64_t out_hi[106], int64_t out_lo[106]) {
+    if (!ctx) return PHMM_E_ARG;
+    if (!out_hi || !out_lo) return fail(ctx, PHMM_E_ARG, "out_hi / out_lo is NULL");
+    if (!ctx->b.prepared || !ctx->b.expect) return fail(ctx, PHMM_E_STATE, "no E-step batch prepared (phmm_expectations_prepare)");
+    try {
+        int rc = do_run(ctx);
+        if (rc) return rc;
+        return expectations_reduce(ctx, out_hi, out_lo);
+    } catch (const std::exception &ex) { return fail(ctx, PHMM_E_NOMEM, ex.what()); }
 }
 
 int phmm_expectations_batch_fixed(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const int64_t *read_off,

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cerrno>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -700,6 +701,69 @@ int guarded(phmm_io *io, F f) {
 extern "C" {
 
 int phmm_io_version(void) { return 1; }
+
+// Estimated DP cells per read from the guide cigars alone (see phmm_io.h).  Same formula as batch.estimate_cells.
+int phmm_io_estimate_cells(int64_t n, const uint32_t *ops, const int64_t *ops_off, const int64_t *read_off, const int64_t *ref_start,
+                           const int64_t *ref_end, int band, int anchor_trim, int64_t split_side, int threads, int64_t *out_cells) {
+    if (n < 0 || (n > 0 && (!ops_off || !read_off || !ref_start || !ref_end || !out_cells))) return PHMM_IO_E_ARG;
+    int hw = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = hw > 0 ? hw : 1;
+    const double e = (double)band, side2 = (double)split_side * (double)split_side;
+    auto block = [&](double dx, double dy) {
+        if (dx < 0) dx = 0;
+        if (dy < 0) dy = 0;
+        if (dx * dy > side2) {
+            const double hx = std::min(std::floor(dx / 2), (double)split_side), hy = std::min(std::floor(dy / 2), (double)split_side);
+            return 2.0 * (hx + e + 1) * (hy + e + 1);
+        }
+        return (dx + e + 1) * (dy + e + 1);
+    };
+    const int64_t chunk = 256;
+    try {
+        parallel_for((n + chunk - 1) / chunk, threads, [&](int64_t c) {
+            for (int64_t i = c * chunk; i < std::min(n, (c + 1) * chunk); i++) {
+                const int64_t lX = ref_end[i] - ref_start[i], lY = read_off[i + 1] - read_off[i];
+                double cost = 0.0;
+                int64_t x = 0, y = 0, px = 0, py = 0;
+                for (int64_t k = ops_off[i]; k < ops_off[i + 1]; k++) {
+                    const int64_t len = ops[k] >> 2;
+                    const int code = (int)(ops[k] & 3u);
+                    if (code == 0) {
+                        if (len > 2 * (int64_t)anchor_trim) {
+                            const int64_t an = len - 2 * anchor_trim;
+                            cost += 2.0 * (double)an * (e + 1);
+                            cost += block((double)(x + anchor_trim - px), (double)(y + anchor_trim - py));
+                            px = x + anchor_trim + an; py = y + anchor_trim + an;
+                        }
+                        x += len; y += len;
+                    } else if (code == 1) y += len;
+                    else if (code == 2) x += len;
+                }
+                cost += block((double)(lX - px), (double)(lY - py));
+                out_cells[i] = cost < 1.0 ? 1 : (int64_t)cost;
+            }
+        });
+    } catch (...) { return PHMM_IO_E_ARG; }
+    return PHMM_IO_OK;
+}
+
+// out[out_off[k] .. out_off[k+1]) = data[off[idx[k]] .. off[idx[k]+1]) (elements of elem_size bytes), threaded.
+int phmm_io_gather_ranges(const void *data, const int64_t *off, const int64_t *idx, int64_t n_idx, int elem_size, int threads,
+                          void *out, const int64_t *out_off) {
+    if (n_idx < 0 || elem_size < 1 || (n_idx > 0 && (!data || !off || !idx || !out || !out_off))) return PHMM_IO_E_ARG;
+    int hw = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = hw > 0 ? hw : 1;
+    const int64_t chunk = 128;
+    try {
+        parallel_for((n_idx + chunk - 1) / chunk, threads, [&](int64_t c) {
+            for (int64_t k = c * chunk; k < std::min(n_idx, (c + 1) * chunk); k++) {
+                const int64_t a = off[idx[k]], b = off[idx[k] + 1];
+                if (b > a) memcpy((char *)out + out_off[k] * elem_size, (const char *)data + a * elem_size, (size_t)(b - a) * elem_size);
+            }
+        });
+    } catch (...) { return PHMM_IO_E_ARG; }
+    return PHMM_IO_OK;
+}
 
 phmm_io *phmm_io_create(int threads) {
     phmm_io *io = new (std::nothrow) phmm_io();

@@ -18,7 +18,7 @@ LIB = os.path.join(_HERE, "libphmm_io.so")
 
 SYMBOLS = ["phmm_io_version", "phmm_io_create", "phmm_io_destroy", "phmm_io_last_error", "phmm_io_load_reference",
            "phmm_io_load_reads", "phmm_io_chain_sam", "phmm_io_load_sam", "phmm_io_counts", "phmm_io_batch_view",
-           "phmm_io_write_sam", "phmm_io_write_realigned_sam"]
+           "phmm_io_write_sam", "phmm_io_write_realigned_sam", "phmm_io_estimate_cells", "phmm_io_gather_ranges"]
 
 
 class IoBatch(C.Structure):
@@ -57,8 +57,41 @@ def load_library():
         L.phmm_io_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.phmm_io_batch_view.argtypes = [C.c_void_p, C.POINTER(IoBatch)]
         L.phmm_io_write_realigned_sam.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64]
+        L.phmm_io_estimate_cells.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_int64, C.c_int, C.c_void_p]
+        L.phmm_io_gather_ranges.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def estimate_cells(in_ops, in_off, read_off, ref_start, ref_end, band, anchor_trim, split_side, threads=0):
+    """int64[n] estimated DP cells per read (phmm_io_estimate_cells)."""
+    n = len(in_off) - 1
+    out = np.zeros(n, dtype=np.int64)
+    a = [np.ascontiguousarray(x, dtype=dt) for x, dt in ((in_ops, np.uint32), (in_off, np.int64), (read_off, np.int64),
+                                                         (ref_start, np.int64), (ref_end, np.int64))]
+    rc = load_library().phmm_io_estimate_cells(n, *[_vp(x) for x in a], int(band), int(anchor_trim), int(split_side), int(threads), _vp(out))
+    if rc != 0:
+        raise PhmmIoError("phmm_io_estimate_cells failed (%d)" % rc)
+    return out
+
+
+def gather_ranges(data, off, idx, threads=0):
+    """(rows idx of the ragged array (data, off) concatenated, new offsets) via phmm_io_gather_ranges."""
+    data = np.ascontiguousarray(data)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    lens = off[idx + 1] - off[idx] if len(idx) else np.zeros(0, dtype=np.int64)
+    new_off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    out = np.empty(int(new_off[-1]), dtype=data.dtype)
+    rc = load_library().phmm_io_gather_ranges(_vp(data), _vp(off), _vp(idx), len(idx), data.dtype.itemsize, int(threads), _vp(out), _vp(new_off))
+    if rc != 0:
+        raise PhmmIoError("phmm_io_gather_ranges failed (%d)" % rc)
+    return out, new_off
 
 
 def _arr(ptr, n, dtype):

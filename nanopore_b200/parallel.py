@@ -6,12 +6,14 @@ Rank 0 runs the host pipeline (SAM in / SAM out, the Target functions of nanopor
 
     set_reference   broadcast of the packed reference            (NCCL broadcast over NVLink)
     set_hmm         broadcast of 25 + 80 model probabilities      (NCCL broadcast)
-    realign         broadcast of the packed batch; every rank realigns its own shard; shards' CIGAR ops are
-                    gathered on rank 0 and put back in input order (the reference re-joins by position,
-                    reference nanopore/analyses/utils.py:597)
-    expectations    every rank runs the E-step on its shard; the exact-integer statistics are summed with one
-                    all-reduce -- integer addition is associative, so 1, 2, 4 and 8 GPUs train the same HMM bit
-                    for bit (the reference sums per-job expectation files in double)
+    set_batch       rank 0 balances the reads on estimated DP cells (longest first) and sends every rank ONLY its
+                    shard (point to point); the shard stays resident on the rank for later calls
+    realign         every rank realigns its shard; CIGAR ops (uint32, and posterior pairs on request) go back to
+                    rank 0 point to point, unpadded, and are put back in input order (the reference re-joins by
+                    position, reference nanopore/analyses/utils.py:597)
+    expectations    every rank runs the E-step on its resident shard; the exact-integer statistics are summed with
+                    one all-reduce -- integer addition is associative, so 1, 2, 4 and 8 GPUs train the same HMM
+                    bit for bit (the reference sums per-job expectation files in double)
 
 The reference has no collectives at all: its only parallelism is jobTree's one-job-per-read task farm
 (utils.py:565-570).  Backend: NCCL when CUDA is present, gloo otherwise (CPU tests of this logic).
@@ -23,11 +25,11 @@ import torch
 import torch.distributed as dist
 
 from . import capi
-from .batch import Batch
+from .batch import Batch, estimate_cells
 from .engine import FixedStats, Realigner
 from .hmm import Hmm
 
-CMD_EXIT, CMD_SET_REF, CMD_SET_HMM, CMD_REALIGN, CMD_EXPECT = range(5)
+CMD_EXIT, CMD_SET_REF, CMD_SET_HMM, CMD_SET_BATCH, CMD_REALIGN, CMD_EXPECT = range(6)
 
 
 def init(backend=None):
@@ -50,40 +52,82 @@ def _device():
 def shard_reads(cost, world):
     """Longest-processing-time-first greedy: reads sorted by descending cost (stable) go to the least loaded
     rank (ties: lowest rank).  Returns one ascending index array per rank.  Deterministic."""
+    import heapq
     cost = np.asarray(cost, dtype=np.int64)
     order = np.argsort(-cost, kind="stable")
-    load = [0] * world
+    heap = [(0, r) for r in range(world)]
     parts = [[] for _ in range(world)]
     for i in order:
-        r = min(range(world), key=lambda k: (load[k], k))
+        load, r = heapq.heappop(heap)
         parts[r].append(int(i))
-        load[r] += int(cost[i])
+        heapq.heappush(heap, (load + int(cost[i]), r))
     return [np.array(sorted(p), dtype=np.int64) for p in parts]
 
 
-def read_cost(batch):
-    """Proxy for DP cells: anti-diagonals of the read's matrix (the band width is the same for all reads)."""
-    return (batch.read_off[1:] - batch.read_off[:-1]) + (batch.ref_end - batch.ref_start)
+def read_cost(batch, params=None):
+    """Estimated DP cells of every read (batch.estimate_cells): what a rank's time is proportional to.  Anti-diagonals
+    alone are the wrong proxy when band widths differ between reads (mixed lengths, sparse anchors)."""
+    if params is None:
+        return estimate_cells(batch)
+    return estimate_cells(batch, params.band, params.anchor_trim, params.split_side)
 
 
-def _bcast_array(a, src=0):
-    """Broadcasts a numpy array (dtype and size known only on src)."""
+# ---- wire format: a list of numpy arrays <-> one uint8 blob (sizes and dtypes in an int64 header) ----
+_DT = [np.dtype(np.uint8), np.dtype(np.int64), np.dtype(np.uint32), np.dtype(np.float64), np.dtype(np.int32)]
+
+
+def _pack(arrays):
+    arrays = [np.ascontiguousarray(a) for a in arrays]
+    head = np.array([len(arrays)] + [v for a in arrays for v in (_DT.index(a.dtype), a.size)], dtype=np.int64)
+    parts = [np.array([head.size], dtype=np.int64).view(np.uint8), head.view(np.uint8)]
+    for a in arrays:
+        raw = a.view(np.uint8).reshape(-1)
+        parts.append(raw)
+        if raw.size % 8:
+            parts.append(np.zeros(8 - raw.size % 8, dtype=np.uint8))      # keep every array 8-byte aligned
+    return np.concatenate(parts)
+
+
+def _unpack(blob):
+    hs = int(blob[:8].view(np.int64)[0])
+    head = blob[8:8 + 8 * hs].view(np.int64)
+    out, o = [], 8 + 8 * hs
+    for k in range(int(head[0])):
+        dt, n = _DT[int(head[1 + 2 * k])], int(head[2 + 2 * k])
+        nb = n * dt.itemsize
+        out.append(blob[o:o + nb].view(dt).copy())
+        o += nb + (-nb) % 8
+    return out
+
+
+def _send_blob(blob, dst):
     dev = _device()
-    meta = torch.zeros(2, dtype=torch.int64, device=dev)
-    codes = {np.dtype(np.uint8): 0, np.dtype(np.int64): 1, np.dtype(np.uint32): 2, np.dtype(np.float64): 3, np.dtype(np.int32): 4}
-    back = {v: k for k, v in codes.items()}
+    dist.send(torch.tensor([blob.size], dtype=torch.int64, device=dev), dst)
+    if blob.size:
+        dist.send(torch.from_numpy(blob).to(dev), dst)
+
+
+def _recv_blob(src):
+    dev = _device()
+    n = torch.zeros(1, dtype=torch.int64, device=dev)
+    dist.recv(n, src)
+    t = torch.empty(int(n[0]), dtype=torch.uint8, device=dev)
+    if int(n[0]):
+        dist.recv(t, src)
+    return t.cpu().numpy()
+
+
+def _bcast_arrays(arrays, src=0):
+    """Broadcast of a list of numpy arrays (known only on src) as one blob."""
+    dev = _device()
+    n = torch.zeros(1, dtype=torch.int64, device=dev)
     if dist.get_rank() == src:
-        a = np.ascontiguousarray(a)
-        meta[0], meta[1] = a.size, codes[a.dtype]
-    dist.broadcast(meta, src)
-    n, dt = int(meta[0]), back[int(meta[1])]
-    if dist.get_rank() == src:
-        t = torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(dev)
-    else:
-        t = torch.empty(n * dt.itemsize, dtype=torch.uint8, device=dev)
-    if n:
-        dist.broadcast(t, src)
-    return t.cpu().numpy().view(dt).copy()
+        blob = _pack(arrays)
+        n[0] = blob.size
+    dist.broadcast(n, src)
+    t = torch.from_numpy(blob).to(dev) if dist.get_rank() == src else torch.empty(int(n[0]), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src)
+    return _unpack(t.cpu().numpy())
 
 
 def _params_to_array(p):
@@ -96,38 +140,21 @@ def _params_from_array(a):
                                tb_diags=int(a[4]), threshold=float(a[5]), gap_gamma=float(a[6]), match_gamma=float(a[7]))
 
 
-def _bcast_batch(batch):
-    arrs = []
-    for name in ("reads", "read_off", "ref_start", "ref_end", "in_ops", "in_off"):
-        arrs.append(_bcast_array(getattr(batch, name) if batch is not None else None))
-    return arrs
-
-
-def _gather_to_root(a, dtype):
-    """Variable-length gather of one array per rank on rank 0 (all_gather of sizes, then padded all_gather)."""
-    dev = _device()
-    world = dist.get_world_size()
-    a = np.ascontiguousarray(a, dtype=dtype)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([a.size], dtype=torch.int64, device=dev))
-    sizes = [int(s) for s in sizes]
-    m = max(max(sizes), 1)
-    buf = np.zeros(m, dtype=np.int64)
-    buf[:a.size] = a.astype(np.int64)
-    outs = [torch.empty(m, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(outs, torch.from_numpy(buf).to(dev))
-    return [o.cpu().numpy()[:s].astype(dtype) for o, s in zip(outs, sizes)]
+_BATCH_FIELDS = ("reads", "read_off", "ref_start", "ref_end", "in_ops", "in_off")
 
 
 class _RankLocal:
-    """What every rank does with its shard."""
+    """What every rank does with its shard.  The shard stays on the rank until rank 0 sends another one, so an EM run
+    (hundreds of E-steps over the same alignments, utils.py:509-523) moves the reads once."""
 
     def __init__(self, local_factory):
         self.local = local_factory()
         self.ref = None
+        self.sub = None
 
     def set_reference(self, codes):
         self.ref = codes
+        self.sub = None
         self.local.set_reference(codes)
 
     def set_hmm(self, arr):
@@ -138,26 +165,27 @@ class _RankLocal:
             h.transitions, h.emissions = arr[1:26].tolist(), arr[26:106].tolist()
             self.local.set_hmm(h)
 
-    def shard(self, arrs):
-        full = Batch(self.ref, *arrs)
-        idx = shard_reads(read_cost(full), dist.get_world_size())[dist.get_rank()]
-        return full, idx, full.subset(idx)
+    def set_batch(self, arrs):
+        self.sub = Batch(self.ref, *arrs)
 
-    def realign(self, arrs, params):
-        full, idx, sub = self.shard(arrs)
+    def realign(self, params, want_posteriors):
+        """-> [ops, off, cells, (posterior off, ref_pos, read_pos, prob_1e7)] of this rank's shard."""
+        sub = self.sub
         if sub.n:
-            ops, off, _ = self.local.realign(sub, params)
+            ops, off, post = self.local.realign(sub, params, want_posteriors=want_posteriors)
         else:
             ops, off = np.zeros(0, np.uint32), np.zeros(1, np.int64)
-        g_idx = _gather_to_root(idx, np.int64)
-        g_ops = _gather_to_root(ops, np.uint32)
-        g_off = _gather_to_root(off, np.int64)
-        g_cells = _gather_to_root(np.array([getattr(self.local, "cells", 0)]), np.int64)
-        return full.n, g_idx, g_ops, g_off, int(sum(int(c[0]) for c in g_cells))
+            post = {"off": np.zeros(1, np.int64), "ref_pos": np.zeros(0, np.int32), "read_pos": np.zeros(0, np.int32),
+                    "prob_1e7": np.zeros(0, np.int32)} if want_posteriors else None
+        out = [np.asarray(ops, dtype=np.uint32), np.asarray(off, dtype=np.int64),
+               np.array([getattr(self.local, "cells", 0) if sub.n else 0], dtype=np.int64)]
+        if want_posteriors:
+            out += [np.asarray(post["off"], np.int64), np.asarray(post["ref_pos"], np.int32),
+                    np.asarray(post["read_pos"], np.int32), np.asarray(post["prob_1e7"], np.int32)]
+        return out
 
-    def expectations(self, arrs, params):
-        _, _, sub = self.shard(arrs)
-        st = self.local.expectations(sub, params) if sub.n else FixedStats()
+    def expectations(self, params):
+        st = self.local.expectations(self.sub, params) if self.sub.n else FixedStats()
         t = torch.from_numpy(st.as_tensor_array()).to(_device())
         dist.all_reduce(t, op=dist.ReduceOp.SUM)                    # 212 x int64: exact, order independent
         return FixedStats.from_tensor_array(t.cpu().numpy())
@@ -167,6 +195,22 @@ def _default_local_factory():
     return Realigner(device=torch.cuda.current_device())
 
 
+def _concat_ranges(per_rank_data, per_rank_off, g_idx, n, dtype):
+    """Re-joins per-rank ragged results in input order: read g_idx[r][k] owns data_r[off_r[k]:off_r[k+1]]."""
+    lens = np.zeros(n, dtype=np.int64)
+    for idx, off in zip(g_idx, per_rank_off):
+        lens[idx] = off[1:] - off[:-1]
+    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    out = np.zeros(int(off[-1]), dtype=dtype)
+    for idx, data, o in zip(g_idx, per_rank_data, per_rank_off):
+        if len(idx) == 0 or o[-1] == 0:
+            continue
+        ln = o[1:] - o[:-1]
+        dst = np.arange(int(o[-1]), dtype=np.int64) + np.repeat(off[idx] - o[:-1], ln)
+        out[dst] = data
+    return out, off
+
+
 class ShardedRealigner:
     """Rank 0's handle; same interface as engine.Realigner."""
 
@@ -174,6 +218,7 @@ class ShardedRealigner:
         assert dist.get_rank() == 0, "ShardedRealigner lives on rank 0; other ranks run worker_loop()"
         self._rl = _RankLocal(local_factory or _default_local_factory)
         self.cells = 0
+        self._sent = None              # (batch, cost parameters, shards) of the batch the ranks hold
         self.set_hmm(hmm)
 
     def _cmd(self, c):
@@ -182,7 +227,8 @@ class ShardedRealigner:
 
     def set_reference(self, codes):
         self._cmd(CMD_SET_REF)
-        self._rl.set_reference(_bcast_array(np.ascontiguousarray(codes, dtype=np.uint8)))
+        self._sent = None
+        self._rl.set_reference(_bcast_arrays([np.ascontiguousarray(codes, dtype=np.uint8)])[0])
 
     def set_hmm(self, hmm):
         self._cmd(CMD_SET_HMM)
@@ -191,26 +237,44 @@ class ShardedRealigner:
         else:
             t, e = hmm.arrays()
             arr = np.concatenate(([float(hmm.type)], t, e))
-        self._rl.set_hmm(_bcast_array(arr))
+        self._rl.set_hmm(_bcast_arrays([arr])[0])
+
+    def _ensure_batch(self, batch, params):
+        """Scatters the batch: every rank receives ONLY its shard (cost-balanced on estimated DP cells), once."""
+        key = (params.band, params.anchor_trim, params.split_side)
+        if self._sent is not None and self._sent[0] is batch and self._sent[1] == key:
+            return self._sent[2]
+        self._cmd(CMD_SET_BATCH)
+        shards = shard_reads(read_cost(batch, params), dist.get_world_size())
+        for r in range(1, dist.get_world_size()):
+            sub = batch.subset(shards[r])
+            _send_blob(_pack([getattr(sub, f) for f in _BATCH_FIELDS]), r)
+        sub0 = batch.subset(shards[0])
+        self._rl.set_batch([getattr(sub0, f) for f in _BATCH_FIELDS])
+        self._sent = (batch, key, shards)
+        return shards
 
     def realign(self, batch, params, want_posteriors=False):
-        if want_posteriors:
-            raise NotImplementedError("posterior pairs are returned by the single-GPU Realigner only")
+        shards = self._ensure_batch(batch, params)
         self._cmd(CMD_REALIGN)
-        p = _params_from_array(_bcast_array(_params_to_array(params)))
-        n, g_idx, g_ops, g_off, self.cells = self._rl.realign(_bcast_batch(batch), p)
-        per_read = [None] * n
-        for idx, ops, off in zip(g_idx, g_ops, g_off):
-            for k, i in enumerate(idx):
-                per_read[int(i)] = ops[off[k]:off[k + 1]]
-        off = np.concatenate(([0], np.cumsum([len(o) for o in per_read]))).astype(np.int64)
-        ops = np.concatenate(per_read) if n else np.zeros(0, np.uint32)
-        return ops.astype(np.uint32), off, None
+        _bcast_arrays([_params_to_array(params), np.array([1 if want_posteriors else 0], dtype=np.int64)])
+        res = [self._rl.realign(params, want_posteriors)]
+        for r in range(1, dist.get_world_size()):
+            res.append(_unpack(_recv_blob(r)))                      # only rank 0 receives; nothing is padded or widened
+        self.cells = int(sum(int(x[2][0]) for x in res))
+        ops, off = _concat_ranges([x[0] for x in res], [x[1] for x in res], shards, batch.n, np.uint32)
+        post = None
+        if want_posteriors:
+            post = {}
+            for k, name in ((4, "ref_pos"), (5, "read_pos"), (6, "prob_1e7")):
+                post[name], post["off"] = _concat_ranges([x[k] for x in res], [x[3] for x in res], shards, batch.n, np.int32)
+        return ops, off, post
 
     def expectations(self, batch, params):
+        self._ensure_batch(batch, params)
         self._cmd(CMD_EXPECT)
-        p = _params_from_array(_bcast_array(_params_to_array(params)))
-        return self._rl.expectations(_bcast_batch(batch), p)
+        _bcast_arrays([_params_to_array(params)])
+        return self._rl.expectations(params)
 
     def close(self):
         """Closes rank 0's local context; workers stay up for the next ShardedRealigner (shutdown() ends them)."""
@@ -238,15 +302,16 @@ def worker_loop(local_factory=None):
         if rl is None:
             rl = _RankLocal(factory)
         if c == CMD_SET_REF:
-            rl.set_reference(_bcast_array(None))
+            rl.set_reference(_bcast_arrays(None)[0])
         elif c == CMD_SET_HMM:
-            rl.set_hmm(_bcast_array(None))
+            rl.set_hmm(_bcast_arrays(None)[0])
+        elif c == CMD_SET_BATCH:
+            rl.set_batch(_unpack(_recv_blob(0)))
         elif c == CMD_REALIGN:
-            p = _params_from_array(_bcast_array(None))
-            rl.realign(_bcast_batch(None), p)
+            pa, wp = _bcast_arrays(None)
+            _send_blob(_pack(rl.realign(_params_from_array(pa), bool(wp[0]))), 0)
         elif c == CMD_EXPECT:
-            p = _params_from_array(_bcast_array(None))
-            rl.expectations(_bcast_batch(None), p)
+            rl.expectations(_params_from_array(_bcast_arrays(None)[0]))
         else:
             raise RuntimeError("unknown command %d" % c)
 

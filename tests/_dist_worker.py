@@ -28,7 +28,10 @@ def main():
     sr = parallel.ShardedRealigner(None, local_factory)
     sr.set_reference(b.ref)
     ops, off, _ = sr.realign(b, p)
+    _, _, post = sr.realign(b, p, want_posteriors=True)       # the shards are resident: nothing is sent again
     st = sr.expectations(b, p)
+    st_again = sr.expectations(b, p)                          # EM calls this hundreds of times on the same batch
+    assert st_again == st
     from nanopore_b200.hmm import Hmm
     h = Hmm.loadHmm(os.path.join(HERE, "golden", "blasr_hmm_0.txt"))
     sr.set_hmm(h)
@@ -37,7 +40,8 @@ def main():
     parallel.shutdown()
     shards = [s.tolist() for s in parallel.shard_reads(parallel.read_cost(b), world)]
     json.dump({"ops": ops.tolist(), "off": off.tolist(), "hi": st.hi.tolist(), "lo": st.lo.tolist(), "cells": sr.cells,
-               "ops_trained": ops2.tolist(), "off_trained": off2.tolist(), "shards": shards}, open(out_path, "w"))
+               "ops_trained": ops2.tolist(), "off_trained": off2.tolist(), "shards": shards,
+               "post": {k: v.tolist() for k, v in post.items()}}, open(out_path, "w"))
 
 
 if __name__ == "__main__":

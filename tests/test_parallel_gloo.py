@@ -30,6 +30,9 @@ def test_shard_reads_is_balanced_and_deterministic():
     parts = parallel.shard_reads(cost, 3)
     assert sorted(np.concatenate(parts).tolist()) == list(range(8))
     loads = [int(cost[p].sum()) for p in parts]
+    b = synth.make_batch(5, 0, 3000, seed=3, lengths=[200, 2000, 200, 900, 50])
+    est = parallel.read_cost(b, capi.default_params(band=10))
+    assert est[1] > est[3] > est[0] > est[4] > 0                       # the cost follows the DP cells, not the window
     assert max(loads) == 300 and sorted(loads)[0] >= 160                 # LPT: the long read alone, the rest split
     assert all(np.array_equal(a, b) for a, b in zip(parts, parallel.shard_reads(cost, 3)))
     assert all((np.diff(p) > 0).all() for p in parts if len(p) > 1)      # input order inside a shard
@@ -57,6 +60,9 @@ def test_world_size_2_matches_single_rank(tmp_path):
     r.set_reference(b.ref)
     ops, off, _ = r.realign(b, p)
     assert got["ops"] == ops.tolist() and got["off"] == off.tolist() and got["cells"] == r.cells
+    _, _, post = r.realign(b, p, want_posteriors=True)              # posterior pairs come back through the shards too
+    assert all(got["post"][k] == post[k].tolist() for k in ("off", "ref_pos", "read_pos", "prob_1e7"))
+    assert len(got["post"]["ref_pos"]) > 0
     st = r.expectations(b, p)
     assert FixedStats(got["hi"], got["lo"]) == st                        # exact: independent of the sharding
     r.set_hmm(Hmm.loadHmm(os.path.join(HERE, "golden", "blasr_hmm_0.txt")))
