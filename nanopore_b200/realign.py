@@ -290,7 +290,11 @@ def loadHmmOrNone(hmmFile):
     return Hmm.loadHmm(hmmFile) if hmmFile is not None else None
 
 
-def realignParams(gapGamma, matchGamma, band=REALIGN_DIAGONAL_EXPANSION, split=REALIGN_SPLIT_MATRIX_BIGGER_THAN):
+def realignParams(gapGamma, matchGamma, band=None, split=None):
+    """The knobs of the cactus_realign command line (utils.py:587); the module constants are read at call time so that
+    a driver (bench.py: band 50 per BASELINE.json) can set them the way the reference edits its literal string."""
+    band = REALIGN_DIAGONAL_EXPANSION if band is None else band
+    split = REALIGN_SPLIT_MATRIX_BIGGER_THAN if split is None else split
     return capi.default_params(band=band, split_side=split, gap_gamma=float(gapGamma), match_gamma=float(matchGamma))
 
 
