@@ -22,6 +22,11 @@ using namespace phmm;
 
 namespace {
 
+// Both base arrays carry BASE_PAD bytes of N (code 4) either side: the unguarded cell loops of k_fb2 read the base before
+// a region's first and after its last without a range test (the transitions those bases would emit start or end outside
+// the matrix, i.e. at -inf, so the value does not matter; the address must be valid).
+constexpr size_t BASE_PAD = 16;
+
 thread_local std::string g_create_error;
 thread_local int64_t g_held_bytes = 0;      // device bytes held by DevBufs of this thread's contexts
 
@@ -358,7 +363,7 @@ int plan_memory(phmm_ctx *ctx) {
         // one 16-byte record per diagonal of every region (k_records)
         b.rec_off.assign(nreg + 1, 0);
         for (int64_t i = 0; i < nreg; i++) b.rec_off[i + 1] = b.rec_off[i] + (int64_t)b.regions[i].lx + b.regions[i].ly + 1;
-        b.fb2_smem = (size_t)2 * CS * b.wcap * 8 + FB2_TAB * 8 + 2 * FB2_RQ * sizeof(DiagRec);
+        b.fb2_smem = (size_t)2 * CS * b.wcap * 8;      // the diagonal buffers; tables and record FIFOs are static
         occ = fb2_occupancy(b.nw, sw, b.expect, b.fb2_smem);
         if (occ < 1) return fail(ctx, PHMM_E_CUDA, "k_fb2 does not fit on this device");
         slot_bytes = b.ring_doubles * 8 + (int64_t)4 * NS * b.wg * 8 +
@@ -482,7 +487,7 @@ int do_prepare(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const 
     if (nreg == 0) { b.prepared = true; return PHMM_OK; }
 
     const int64_t total_read = n_reads ? read_off[n_reads] : 0;
-    CK(ctx->d_reads.ensure((size_t)total_read + 16));
+    CK(ctx->d_reads.ensure((size_t)total_read + 2 * BASE_PAD));
     CK(ctx->d_regions.ensure((size_t)nreg * sizeof(Region)));
     CK(ctx->d_runs.ensure((size_t)(b.runs.size() + 1) * sizeof(Run)));
     CK(ctx->d_geom.ensure((size_t)nreg * sizeof(RegionGeom)));
@@ -498,7 +503,8 @@ int do_prepare(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const 
     CK(ctx->d_tbp.ensure((size_t)b.tb_off[nreg] * 4 + 16));
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_tboff.p, b.tb_off.data(), (size_t)(nreg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (total_read) CK(cudaMemcpyAsync(ctx->d_reads.p, read_bases, (size_t)total_read, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_reads.p, 4, (size_t)total_read + 2 * BASE_PAD, ctx->stream));
+    if (total_read) CK(cudaMemcpyAsync(ctx->d_reads.as<uint8_t>() + BASE_PAD, read_bases, (size_t)total_read, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_regions.p, b.regions.data(), nreg * sizeof(Region), cudaMemcpyHostToDevice, ctx->stream));
     if (!b.runs.empty()) CK(cudaMemcpyAsync(ctx->d_runs.p, b.runs.data(), b.runs.size() * sizeof(Run), cudaMemcpyHostToDevice, ctx->stream));
     k_geometry<<<(unsigned)((nreg + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_regions.as<Region>(), ctx->d_runs.as<Run>(), (int)nreg, b.dp,
@@ -536,7 +542,7 @@ int do_run(phmm_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
     FbArgs fa;
     memset(&fa, 0, sizeof(fa));
-    fa.ref = ctx->d_ref.as<uint8_t>(); fa.reads = ctx->d_reads.as<uint8_t>();
+    fa.ref = ctx->d_ref.as<uint8_t>() + BASE_PAD; fa.reads = ctx->d_reads.as<uint8_t>() + BASE_PAD;
     fa.regions = ctx->d_regions.as<Region>(); fa.runs = ctx->d_runs.as<Run>(); fa.order = ctx->d_order.as<int32_t>();
     fa.n_regions = (int32_t)nreg; fa.counter = ctx->d_counter.as<int32_t>();
     fa.m = ctx->model; fa.p = b.dp;
@@ -711,8 +717,9 @@ int phmm_set_reference(phmm_ctx *ctx, const uint8_t *bases, int64_t n) {
     if (!ctx) return PHMM_E_ARG;
     if (n < 0 || (n > 0 && !bases)) return fail(ctx, PHMM_E_ARG, "bad reference");
     CK(cudaSetDevice(ctx->device));
-    CK(ctx->d_ref.ensure((size_t)n + 16));
-    if (n) CK(cudaMemcpy(ctx->d_ref.p, bases, (size_t)n, cudaMemcpyHostToDevice));
+    CK(ctx->d_ref.ensure((size_t)n + 2 * BASE_PAD));
+    CK(cudaMemset(ctx->d_ref.p, 4, (size_t)n + 2 * BASE_PAD));
+    if (n) CK(cudaMemcpy(ctx->d_ref.as<uint8_t>() + BASE_PAD, bases, (size_t)n, cudaMemcpyHostToDevice));
     ctx->ref_len = n;
     ctx->b.prepared = false; ctx->b.ran = false;
     return PHMM_OK;

@@ -57,6 +57,19 @@ constexpr int FB2_TAB = 16 + 25 * TS + 5 * TS + 5 * TS;   // logAdd coefficients
 #define FB2_DBG(bits) false
 #endif
 
+// Rotation of the warp -> cells assignment within a diagonal (fast paths): warp k takes the cells [32 (k ^ r), ..) with
+// r = diagonal mod NW.  Hardware warp w of a block runs on scheduler w % 4; without the rotation warp 0 of every resident
+// block takes the extra round of each diagonal wider than the block and its scheduler saturates while the others idle
+// at the barrier (profiles/r02a_k_fb2_ncu_metrics.txt: issue active 92 % max, 30 % min over the schedulers).
+#ifndef PHMM_NO_ROT
+#define FB2_ROT(diag) ((((diag) >> FB2_ROT_SHIFT) & (NW - 1)) << 5)
+#else
+#define FB2_ROT(diag) 0
+#endif
+#ifndef FB2_ROT_SHIFT
+#define FB2_ROT_SHIFT 0
+#endif
+
 struct Fb2Args {
     const uint8_t *ref;
     const uint8_t *reads;
@@ -107,7 +120,11 @@ __device__ __forceinline__ double logadd_t(double x, double y, const char *ctab)
     const double2 c32 = *reinterpret_cast<const double2 *>(ctab + off);
     const double2 c10 = *reinterpret_cast<const double2 *>(ctab + off + 16);
     const double r = fma(fma(fma(c32.x, t, c32.y), t, c10.x), t, c10.y) + mn;
+#if PHMM_RANGE_INT
     return ((unsigned)dh * 2u < 0x401E0000u * 2u) ? r : mx;      // |d| < 7.5; false for inf / NaN
+#else
+    return (t < 7.5) ? r : mx;                                   // false for inf / NaN (the smaller operand is -inf)
+#endif
 }
 
 // Shared-memory tables of (emission + transition) sums, one padded row of CS doubles per symbol (pair); the
@@ -366,9 +383,12 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
     const int tid = threadIdx.x;
     const int wcap = a.wcap, cmask = wcap - 1;
     double *const sbuf = reinterpret_cast<double *>(smem_raw);                  // [2][wcap][CS]
-    double *const sct = sbuf + 2 * CS * wcap;                                    // 4 rows x (c3 c2 c1 c0)
+    // tables and record FIFOs at link-time constant shared addresses: their offsets fold into the LDS immediates
+    __shared__ __align__(16) double s_tab[FB2_TAB];
+    __shared__ __align__(16) DiagRec s_rec[2 * FB2_RQ];
+    double *const sct = s_tab;                                                   // 4 rows x (c3 c2 c1 c0)
     double *const stM = sct + 16, *const stX = stM + 25 * TS, *const stY = stX + 5 * TS;
-    DiagRec *const srec = reinterpret_cast<DiagRec *>(sct + FB2_TAB);            // [2][FB2_RQ]
+    DiagRec *const srec = s_rec;                                                 // [2][FB2_RQ]
     __shared__ int s_region;
     __shared__ int s_npairs;
     __shared__ double s_est;                           // total of the window's first posterior diagonal
@@ -496,11 +516,12 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                         double *const b0 = sbuf + par * wcap * CS;
                         const double *const b1 = sbuf + (par ^ 1) * wcap * CS;
                         const int dl = par ? -1 : 0;                  // lower is in column c-1 (odd d) or c (even d); upper one further
-                        for (int i = tid; i < w; i += NC) {
+                        // which warp takes which 32 cells rotates with the diagonal: the warps that get a second (third ..)
+                        // round of a diagonal wider than the block sit on all four schedulers of the SM in turn
+                        for (int i = tid ^ FB2_ROT(d); i < w; i += NC) {
                             const int x = xlo + i, y = d - x;
-                            int cX, cY;
-                            if (FB2_DBG(1)) { cX = x & 3; cY = y & 3; }
-                            else { cX = x >= 1 ? X[x - 1] : 4; cY = y >= 1 ? Y[y - 1] : 4; }
+                            // x = 0 / y = 0: the byte before the region (padded arrays); it only meets -inf predecessors
+                            const int cX = X[x - 1], cY = Y[y - 1];
                             const int c = clo + i;
                             double *const p0 = b0 + (c & cmask) * CS;                      // own column == middle's
                             const double *const pl = b1 + ((c + dl) & cmask) * CS;
@@ -602,10 +623,9 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                                     double *const b0 = sbuf + bpar * wcap * CS;
                                     const double *const b1 = sbuf + (bpar ^ 1) * wcap * CS;
                                     const int du = bpar ? -1 : 0;     // (x, y+1) is in column c-1 (odd dd) or c (even dd); (x+1, y) one further
-                                    for (int i = tid; i < rb.w; i += NC) {
+                                    for (int i = tid ^ FB2_ROT(dd); i < rb.w; i += NC) {
                                         const int x = rb.xlo + i, y = dd - x;
-                                        const int cXn = x < lx ? X[x] : 4;
-                                        const int cYn = y < ly ? Y[y] : 4;
+                                        const int cXn = X[x], cYn = Y[y];              // x = lx / y = ly: the byte after the region, meets -inf only
                                         const int c = bclo + i;
                                         const double fM = rg[i];                                   // issued early, used last
                                         double *const p0 = b0 + (c & cmask) * CS;                  // own column == (x+1, y+1)'s

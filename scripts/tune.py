@@ -9,7 +9,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from nanopore_b200 import capi, synth
 _tune = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "libphmm_tune.so")
-if os.path.exists(_tune) and os.environ.get("SHIPPED_LIB") != "1":
+if os.environ.get("TUNE_LIB"):                       # a variant built by scripts/build_variant.sh
+    capi.LIB_PATH = os.path.abspath(os.environ["TUNE_LIB"])
+elif os.path.exists(_tune) and os.environ.get("SHIPPED_LIB") != "1":
     capi.LIB_PATH = _tune
 
 n = int(sys.argv[1])
