@@ -181,6 +181,23 @@ int phmm_batch_run(phmm_ctx *ctx);
 int phmm_batch_fetch(phmm_ctx *ctx, uint32_t **out_cigar_ops, int64_t **out_cigar_off, phmm_posteriors *post);
 int phmm_batch_get_stats(phmm_ctx *ctx, phmm_batch_stats *out);
 
+/* Replaces: parsing every read's --outputAllPosteriorProbs file and summing prob into
+ * expectationsOfBasesAtEachPosition[(ref, refPos)][readBase] (marginAlignSnpCaller.py:136-155), the heaviest
+ * consumer of the kernel (4 HMMs x 13 coverage samples, marginAlignSnpCaller.py:46-48).  The table lives on the
+ * device: 5 sums (read base A, C, G, T, other -- the reference creates a position's entry for any pair but adds only
+ * ACGT read bases to it; the fifth column keeps that distinction) per base of the array given to
+ * phmm_set_reference, in the 1e-7 units of phmm_posteriors, accumulated with integer atomics over
+ * every batch added since the last reset -- exact and independent of the order of pairs, batches, ranks and GPUs
+ * (ranks add their int64 tables).  The posterior pairs never leave the GPU.
+ *   reset  sizes n_tables tables for the current reference and zeroes them;
+ *   add    after phmm_batch_prepare [+ phmm_batch_run]: adds the pairs of the prepared batch to `table`; read_mask
+ *          (one byte per read of that batch, NULL = all) selects the reads that count, so the coverage samples of
+ *          the caller (one table each) share one resident set of posteriors;
+ *   fetch  copies one table out; n must be 5 x the reference length. */
+int phmm_base_expectations_reset(phmm_ctx *ctx, int32_t n_tables);
+int phmm_batch_add_base_expectations(phmm_ctx *ctx, const uint8_t *read_mask, int32_t table);
+int phmm_base_expectations_fetch(phmm_ctx *ctx, int32_t table, int64_t *out, int64_t n);
+
 /* Upper bound on device bytes the library may hold for scratch (0 = 80% of
  * free memory at first use). */
 int phmm_set_memory_budget(phmm_ctx *ctx, int64_t bytes);

@@ -34,6 +34,13 @@ def system(command):
     return sts
 
 
+def prettyXml(elem):
+    """Indented text of an ElementTree element (sonLib bioio.prettyXml, used by marginAlignSnpCaller.py:304)."""
+    import xml.etree.ElementTree as ET
+    from xml.dom import minidom
+    return minidom.parseString(ET.tostring(elem, "utf-8")).toprettyxml(indent="  ")
+
+
 def nameValue(name, value, valueType=str):
     """`--name=value`, or the empty string when value is None (utils.py:586)."""
     if valueType == bool:

@@ -23,6 +23,7 @@ EXPORTS = [
     "phmm_expectations_batch", "phmm_expectations_batch_fixed", "phmm_batch_prepare", "phmm_batch_run", "phmm_batch_fetch",
     "phmm_batch_get_stats", "phmm_set_memory_budget", "phmm_set_option", "phmm_free", "phmm_free_posteriors",
     "phmm_expectations_prepare", "phmm_expectations_run_fixed",
+    "phmm_base_expectations_reset", "phmm_batch_add_base_expectations", "phmm_base_expectations_fetch",
 ]
 
 
@@ -91,6 +92,9 @@ def load_library():
     L.phmm_batch_fetch.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_int64)),
                                    C.POINTER(Posteriors)]
     L.phmm_batch_get_stats.argtypes = [vp, C.POINTER(BatchStats)]
+    L.phmm_base_expectations_reset.argtypes = [vp, i32]
+    L.phmm_batch_add_base_expectations.argtypes = [vp, vp, i32]
+    L.phmm_base_expectations_fetch.argtypes = [vp, i32, vp, i64]
     L.phmm_set_memory_budget.argtypes = [vp, i64]
     L.phmm_set_option.argtypes = [vp, C.c_char_p, i64]
     L.phmm_free.argtypes = [vp]
@@ -231,6 +235,25 @@ class PhmmContext:
         s = BatchStats()
         self._check(self._lib.phmm_batch_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def base_expectations_reset(self, n_tables=1):
+        """Sizes and zeroes n_tables device tables of per-reference-position base expectations."""
+        self._check(self._lib.phmm_base_expectations_reset(self._h, int(n_tables)))
+
+    def add_base_expectations(self, read_mask=None, table=0):
+        """Adds the posterior pairs of the prepared batch to a device table; read_mask: one byte per read."""
+        m = None
+        if read_mask is not None:
+            m = np.ascontiguousarray(read_mask, dtype=np.uint8)
+            if m.size != self._n_prepared:
+                raise ValueError("read_mask must have one entry per read of the prepared batch")
+        self._check(self._lib.phmm_batch_add_base_expectations(self._h, _ptr(m) if m is not None else None, int(table)))
+
+    def base_expectations_fetch(self, ref_len, table=0):
+        """-> int64[ref_len, 5] in units of 1e-7 (read base A, C, G, T, other)."""
+        out = np.zeros((int(ref_len), 5), dtype=np.int64)
+        self._check(self._lib.phmm_base_expectations_fetch(self._h, int(table), _ptr(out), out.size))
+        return out
 
     def expectations_batch(self, reads, read_off, ref_start, ref_end, in_ops, in_off, params):
         """Returns float64[106]: 25 transition + 80 emission expectations + log-likelihood."""

@@ -98,6 +98,7 @@ struct phmm_ctx {
     DevBuf d_sumx, d_sumy, d_dstart, d_dfill, d_sidx, d_wre, d_pred, d_colmap, d_sring, d_lring;
     DevBuf d_mrx, d_mry, d_mrn, d_nmruns, d_score;
     DevBuf d_cx, d_cy, d_cn, d_coff;
+    DevBuf d_baseexp, d_readmask; int64_t baseexp_len = -1; int32_t baseexp_tables = 0;   // tables of 5 x reference length sums of posterior mass per read base (A C G T other)
     BatchState b;
 };
 
@@ -721,6 +722,7 @@ int phmm_set_reference(phmm_ctx *ctx, const uint8_t *bases, int64_t n) {
     CK(cudaMemset(ctx->d_ref.p, 4, (size_t)n + 2 * BASE_PAD));
     if (n) CK(cudaMemcpy(ctx->d_ref.as<uint8_t>() + BASE_PAD, bases, (size_t)n, cudaMemcpyHostToDevice));
     ctx->ref_len = n;
+    ctx->baseexp_len = -1; ctx->baseexp_tables = 0;
     ctx->b.prepared = false; ctx->b.ran = false;
     return PHMM_OK;
 }
@@ -918,34 +920,84 @@ int phmm_batch_fetch(phmm_ctx *ctx, uint32_t **out_cigar_ops, int64_t **out_ciga
                 CK(cudaMemcpyAsync(qw.data(), ctx->d_cn.p, tp * 4, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaStreamSynchronize(ctx->stream));
             }
-            int64_t o = 0;
-            std::vector<int64_t> idx;
-            for (int64_t r = 0; r < b.n_reads; r++) {
-                post->off[r] = o;
-                const int64_t o0 = o;
-                for (int64_t g = b.read_first_region[r]; g < b.read_first_region[r + 1]; g++) {
-                    const Region &reg = b.regions[g];
-                    for (int64_t k = poff[g]; k < poff[g + 1]; k++) {
-                        post->ref_pos[o] = reg.x1 + qx[k]; post->read_pos[o] = reg.y1 + qy[k]; post->prob_1e7[o] = qw[k];
+            // per read: its regions' pairs in canonical (ref_pos, read_pos) order; reads are independent -> host threads
+            post->off[0] = 0;
+            for (int64_t r = 0; r < b.n_reads; r++)
+                post->off[r + 1] = post->off[r] + (poff[b.read_first_region[r + 1]] - poff[b.read_first_region[r]]);
+            parallel_reads([&](int64_t r0, int64_t r1) {
+                std::vector<std::pair<uint64_t, int32_t>> tmp;
+                for (int64_t r = r0; r < r1; r++) {
+                    tmp.clear();
+                    for (int64_t g = b.read_first_region[r]; g < b.read_first_region[r + 1]; g++) {
+                        const Region &reg = b.regions[g];
+                        for (int64_t k = poff[g]; k < poff[g + 1]; k++)
+                            tmp.emplace_back(((uint64_t)(uint32_t)(reg.x1 + qx[k]) << 32) | (uint32_t)(reg.y1 + qy[k]), qw[k]);
+                    }
+                    std::sort(tmp.begin(), tmp.end());                 // a cell occurs once: keys are distinct
+                    int64_t o = post->off[r];
+                    for (const auto &e : tmp) {
+                        post->ref_pos[o] = (int32_t)(e.first >> 32); post->read_pos[o] = (int32_t)(uint32_t)e.first; post->prob_1e7[o] = e.second;
                         o++;
                     }
                 }
-                // canonical order within the read: (ref_pos, read_pos)
-                const int64_t m = o - o0;
-                idx.resize(m);
-                std::iota(idx.begin(), idx.end(), 0);
-                std::sort(idx.begin(), idx.end(), [&](int64_t i, int64_t j) {
-                    if (post->ref_pos[o0 + i] != post->ref_pos[o0 + j]) return post->ref_pos[o0 + i] < post->ref_pos[o0 + j];
-                    return post->read_pos[o0 + i] < post->read_pos[o0 + j];
-                });
-                std::vector<int32_t> t0(m), t1(m), t2(m);
-                for (int64_t i = 0; i < m; i++) { t0[i] = post->ref_pos[o0 + idx[i]]; t1[i] = post->read_pos[o0 + idx[i]]; t2[i] = post->prob_1e7[o0 + idx[i]]; }
-                for (int64_t i = 0; i < m; i++) { post->ref_pos[o0 + i] = t0[i]; post->read_pos[o0 + i] = t1[i]; post->prob_1e7[o0 + i] = t2[i]; }
-            }
-            post->off[b.n_reads] = o;
+            });
         }
         return PHMM_OK;
     } catch (const std::exception &ex) { return fail(ctx, PHMM_E_NOMEM, ex.what()); }
+}
+
+int phmm_base_expectations_reset(phmm_ctx *ctx, int32_t n_tables) {
+    if (!ctx) return PHMM_E_ARG;
+    if (ctx->ref_len < 0) return fail(ctx, PHMM_E_STATE, "no reference set");
+    if (n_tables < 1 || n_tables > 4096) return fail(ctx, PHMM_E_ARG, "n_tables must be in 1..4096");
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)n_tables * (size_t)ctx->ref_len * 5 * 8 + 64;
+    CK(ctx->d_baseexp.ensure(bytes));
+    CK(cudaMemsetAsync(ctx->d_baseexp.p, 0, bytes, ctx->stream));
+    ctx->baseexp_len = ctx->ref_len; ctx->baseexp_tables = n_tables;
+    return PHMM_OK;
+}
+
+int phmm_batch_add_base_expectations(phmm_ctx *ctx, const uint8_t *read_mask, int32_t table) {
+    if (!ctx) return PHMM_E_ARG;
+    if (table < 0 || table >= ctx->baseexp_tables) return fail(ctx, PHMM_E_ARG, "no such table (phmm_base_expectations_reset sizes them)");
+    BatchState &b = ctx->b;
+    if (!b.prepared || b.expect) return fail(ctx, PHMM_E_STATE, "no realignment batch prepared");
+    if (ctx->baseexp_len != ctx->ref_len) return fail(ctx, PHMM_E_STATE, "phmm_base_expectations_reset has not been called for this reference");
+    try {
+        CK(cudaSetDevice(ctx->device));
+        const int64_t nreg = (int64_t)b.regions.size();
+        if (nreg == 0) return PHMM_OK;
+        std::vector<int32_t> npairs;
+        int rc = run_until_fits(ctx, npairs);
+        if (rc) return rc;
+        const uint8_t *d_mask = nullptr;
+        if (read_mask) {
+            CK(ctx->d_readmask.ensure((size_t)b.n_reads + 16));
+            CK(cudaMemcpyAsync(ctx->d_readmask.p, read_mask, (size_t)b.n_reads, cudaMemcpyHostToDevice, ctx->stream));
+            d_mask = ctx->d_readmask.as<uint8_t>();
+        }
+        const unsigned grid = (unsigned)std::min<int64_t>(nreg, (int64_t)ctx->sm_count * 16);
+        k_base_expect<<<grid, 256, 0, ctx->stream>>>(ctx->d_regions.as<Region>(), ctx->d_npairs.as<int32_t>(), (int)nreg,
+                                                     ctx->d_reads.as<uint8_t>() + BASE_PAD, d_mask, ctx->d_px.as<int32_t>(),
+                                                     ctx->d_py.as<int32_t>(), ctx->d_pw.as<int32_t>(),
+                                                     ctx->d_baseexp.as<unsigned long long>() + (size_t)table * (size_t)ctx->ref_len * 5);
+        CK(cudaGetLastError());
+        b.stats.launches++;
+        CK(cudaStreamSynchronize(ctx->stream));      // read_mask is the caller's again
+        return PHMM_OK;
+    } catch (const std::exception &ex) { return fail(ctx, PHMM_E_NOMEM, ex.what()); }
+}
+
+int phmm_base_expectations_fetch(phmm_ctx *ctx, int32_t table, int64_t *out, int64_t n) {
+    if (!ctx || !out) return PHMM_E_ARG;
+    if (table < 0 || table >= ctx->baseexp_tables) return fail(ctx, PHMM_E_ARG, "no such table");
+    if (ctx->baseexp_len < 0 || ctx->baseexp_len != ctx->ref_len) return fail(ctx, PHMM_E_STATE, "no base expectations accumulated");
+    if (n != 5 * ctx->ref_len) return fail(ctx, PHMM_E_ARG, "out must hold 5 values per reference base");
+    CK(cudaSetDevice(ctx->device));
+    if (n) CK(cudaMemcpyAsync(out, ctx->d_baseexp.as<unsigned long long>() + (size_t)table * (size_t)n, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PHMM_OK;
 }
 
 int phmm_realign_batch(phmm_ctx *ctx, int64_t n_reads, const uint8_t *read_bases, const int64_t *read_off,

@@ -831,4 +831,27 @@ __global__ void k_compact(const Region *regions, const int32_t *nmruns, const in
     }
 }
 
+// Per-reference-position base expectations (replaces the parse-and-sum loop over every read's
+// --outputAllPosteriorProbs file, reference nanopore/analyses/marginAlignSnpCaller.py:149-155): every posterior pair
+// (x, y, prob) of a region adds prob (1e-7 units) to acc[5 * (reference index of x) + read base at y], columns A C G T
+// and "other": the reference creates the position's entry for any pair and adds only ACGT read bases to it, so the fifth
+// column keeps what it needs to tell "no pair here" from "only non-ACGT pairs here".  One block per region, a pair per thread; integer atomics
+// commute, so the table does not depend on the order of pairs, regions, batches or ranks.  read_mask (one byte per
+// read of the batch, may be NULL) selects the reads that contribute: the caller's coverage samples
+// (marginAlignSnpCaller.py:91-97) reuse one resident set of posteriors.
+__global__ void k_base_expect(const Region *regions, const int32_t *npairs, int n_regions, const uint8_t *reads,
+                              const uint8_t *read_mask, const int32_t *px, const int32_t *py, const int32_t *pw,
+                              unsigned long long *acc) {
+    for (int r = blockIdx.x; r < n_regions; r += gridDim.x) {
+        const Region reg = regions[r];
+        if (read_mask && !read_mask[reg.read]) continue;
+        const int n = min(npairs[r], reg.pair_cap);
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            const int64_t q = reg.pair_off + k;
+            const int b = reads[reg.yoff + py[q]];
+            atomicAdd(&acc[(reg.xoff + px[q]) * 5 + min(b, 4)], (unsigned long long)pw[q]);
+        }
+    }
+}
+
 }  // namespace phmm

@@ -140,6 +140,26 @@ class Realigner:
                     "prob_1e7": np.concatenate([p["prob_1e7"] for p, _ in posts] or [np.zeros(0, np.int32)])}
         return ops, off, post
 
+    def base_expectations(self, batch, params, masks=None):
+        """Per-reference-position sums of posterior match probability by read base (the table
+        marginAlignSnpCaller.py:149-155 builds from every read's --outputAllPosteriorProbs file), accumulated on the
+        device: -> int64[len(masks) or 1, reference length, 5] in units of 1e-7 (read base A C G T other).  masks: boolean arrays over the reads
+        of `batch`, one per sample of reads (coverage replicates); all of them share ONE forward/backward pass."""
+        self._em_batch = None
+        ref_len = len(batch.ref)
+        ms = [None] if masks is None else [np.ascontiguousarray(m, dtype=np.uint8) for m in masks]
+        self.ctx.base_expectations_reset(len(ms))
+        self.cells = 0
+        for a, b in chunk_bounds(batch, self.max_bases, self.max_cells, params):
+            sub = batch if (a, b) == (0, batch.n) else batch.subset(np.arange(a, b))
+            self.ctx.prepare(sub.reads, sub.read_off, sub.ref_start, sub.ref_end, sub.in_ops, sub.in_off, params)
+            self.ctx.run()
+            self.cells += int(self.ctx.stats()["cells"])
+            for k, m in enumerate(ms):
+                if m is None or m[a:b].any():
+                    self.ctx.add_base_expectations(None if m is None else m[a:b], k)
+        return np.stack([self.ctx.base_expectations_fetch(ref_len, k) for k in range(len(ms))])
+
     def expectations(self, batch, params):
         """E-step over the batch -> FixedStats (exact, order independent)."""
         tot = FixedStats()

@@ -14,6 +14,9 @@ Rank 0 runs the host pipeline (SAM in / SAM out, the Target functions of nanopor
     expectations    every rank runs the E-step on its resident shard; the exact-integer statistics are summed with
                     one all-reduce -- integer addition is associative, so 1, 2, 4 and 8 GPUs train the same HMM
                     bit for bit (the reference sums per-job expectation files in double)
+    base_expectations  every rank scatter-adds the posterior pairs of its shard into per-reference-position tables
+                    on its GPU (one table per sample of reads); the int64 tables are summed with one all-reduce
+                    (marginAlignSnpCaller.py:149-155 builds them by parsing one text file per read)
 
 The reference has no collectives at all: its only parallelism is jobTree's one-job-per-read task farm
 (utils.py:565-570).  Backend: NCCL when CUDA is present, gloo otherwise (CPU tests of this logic).
@@ -29,7 +32,7 @@ from .batch import Batch, estimate_cells
 from .engine import FixedStats, Realigner
 from .hmm import Hmm
 
-CMD_EXIT, CMD_SET_REF, CMD_SET_HMM, CMD_SET_BATCH, CMD_REALIGN, CMD_EXPECT = range(6)
+CMD_EXIT, CMD_SET_REF, CMD_SET_HMM, CMD_SET_BATCH, CMD_REALIGN, CMD_EXPECT, CMD_BASE_EXPECT = range(7)
 
 
 def init(backend=None):
@@ -184,6 +187,16 @@ class _RankLocal:
                     np.asarray(post["read_pos"], np.int32), np.asarray(post["prob_1e7"], np.int32)]
         return out
 
+    def base_expectations(self, params, masks):
+        """masks: uint8[n_samples, reads of this shard] -> int64[n_samples, reference length, 5], summed over ranks."""
+        if self.sub.n:
+            t = self.local.base_expectations(self.sub, params, masks=list(masks))
+        else:
+            t = np.zeros((len(masks), len(self.ref), 5), dtype=np.int64)
+        t = torch.from_numpy(np.ascontiguousarray(t)).to(_device())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)                    # int64: exact, independent of the sharding
+        return t.cpu().numpy()
+
     def expectations(self, params):
         st = self.local.expectations(self.sub, params) if self.sub.n else FixedStats()
         t = torch.from_numpy(st.as_tensor_array()).to(_device())
@@ -270,6 +283,17 @@ class ShardedRealigner:
                 post[name], post["off"] = _concat_ranges([x[k] for x in res], [x[3] for x in res], shards, batch.n, np.int32)
         return ops, off, post
 
+    def base_expectations(self, batch, params, masks=None):
+        shards = self._ensure_batch(batch, params)
+        ms = np.ones((1, batch.n), dtype=np.uint8) if masks is None else np.stack([np.asarray(m, dtype=np.uint8) for m in masks])
+        self._cmd(CMD_BASE_EXPECT)
+        _bcast_arrays([_params_to_array(params)])
+        for r in range(1, dist.get_world_size()):
+            _send_blob(_pack([np.ascontiguousarray(ms[:, shards[r]]).reshape(-1), np.array([ms.shape[0]], dtype=np.int64)]), r)
+        out = self._rl.base_expectations(params, np.ascontiguousarray(ms[:, shards[0]]))
+        self.cells = 0
+        return out
+
     def expectations(self, batch, params):
         self._ensure_batch(batch, params)
         self._cmd(CMD_EXPECT)
@@ -312,6 +336,10 @@ def worker_loop(local_factory=None):
             _send_blob(_pack(rl.realign(_params_from_array(pa), bool(wp[0]))), 0)
         elif c == CMD_EXPECT:
             rl.expectations(_params_from_array(_bcast_arrays(None)[0]))
+        elif c == CMD_BASE_EXPECT:
+            pa = _params_from_array(_bcast_arrays(None)[0])
+            m, ns = _unpack(_recv_blob(0))
+            rl.base_expectations(pa, m.reshape(int(ns[0]), -1))
         else:
             raise RuntimeError("unknown command %d" % c)
 

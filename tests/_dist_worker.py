@@ -32,6 +32,8 @@ def main():
     st = sr.expectations(b, p)
     st_again = sr.expectations(b, p)                          # EM calls this hundreds of times on the same batch
     assert st_again == st
+    masks = [np.ones(b.n, np.uint8), np.array([1, 0, 1, 0, 0, 1, 0], np.uint8)]
+    tables = sr.base_expectations(b, p, masks=masks)          # per-rank scatter-add, int64 all-reduce
     from nanopore_b200.hmm import Hmm
     h = Hmm.loadHmm(os.path.join(HERE, "golden", "blasr_hmm_0.txt"))
     sr.set_hmm(h)
@@ -41,7 +43,7 @@ def main():
     shards = [s.tolist() for s in parallel.shard_reads(parallel.read_cost(b), world)]
     json.dump({"ops": ops.tolist(), "off": off.tolist(), "hi": st.hi.tolist(), "lo": st.lo.tolist(), "cells": sr.cells,
                "ops_trained": ops2.tolist(), "off_trained": off2.tolist(), "shards": shards,
-               "post": {k: v.tolist() for k, v in post.items()}}, open(out_path, "w"))
+               "post": {k: v.tolist() for k, v in post.items()}, "tables": tables.tolist()}, open(out_path, "w"))
 
 
 if __name__ == "__main__":

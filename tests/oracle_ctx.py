@@ -58,6 +58,35 @@ class OracleContext:
             self._cells += c
         return hi, lo
 
+    # split form + device tables of base expectations, restated on the host from the checker's posterior pairs
+    def prepare(self, reads, read_off, ref_start, ref_end, in_ops, in_off, params):
+        self._prepared = (np.asarray(reads), np.asarray(read_off), np.asarray(ref_start), np.asarray(ref_end), np.asarray(in_ops),
+                          np.asarray(in_off), params)
+        self._post = None
+
+    def run(self):
+        if self._post is None:
+            self._post = self.realign_batch(*self._prepared, want_posteriors=True)[2]
+
+    def base_expectations_reset(self, n_tables=1):
+        self._tables = np.zeros((n_tables, len(self.ref), 5), dtype=np.int64)
+
+    def add_base_expectations(self, read_mask=None, table=0):
+        self.run()
+        reads, read_off, ref_start = self._prepared[0], self._prepared[1], self._prepared[2]
+        post = self._post
+        for i in range(len(read_off) - 1):
+            if read_mask is not None and not read_mask[i]:
+                continue
+            s = slice(post["off"][i], post["off"][i + 1])
+            b = reads[read_off[i] + post["read_pos"][s].astype(np.int64)]
+            np.add.at(self._tables[table], (ref_start[i] + post["ref_pos"][s].astype(np.int64), np.minimum(b, 4)),
+                      post["prob_1e7"][s].astype(np.int64))
+
+    def base_expectations_fetch(self, ref_len, table=0):
+        assert ref_len == len(self.ref)
+        return self._tables[table].copy()
+
     def stats(self):
         return {"cells": self._cells}
 

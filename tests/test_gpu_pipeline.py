@@ -118,3 +118,52 @@ def test_alignment_uncertainty_on_gpu_equals_checker(tmp_path):
                 realign.setRealignerFactory(prev)
         outs.append(os.path.join(outdir, "alignmentUncertainty.xml"))
     assert filecmp.cmp(outs[0], outs[1], shallow=False)
+
+
+def test_base_expectation_tables_on_gpu_equal_the_host_sum_over_returned_pairs():
+    """k_base_expect (phmm_batch_add_base_expectations): the device scatter-add of posterior mass by reference position
+    and read base equals, as integers, the host sum over the pairs phmm_posteriors returns -- with read masks, with N
+    read bases, and when the batch is cut into several library calls."""
+    b = synth.make_batch(40, 600, 3000, seed=77)
+    b.reads[::53] = 4                                                   # N read bases go to the fifth column
+    p = posteriors.posteriorParams()
+    r = Realigner()
+    r.set_reference(b.ref)
+    rng = np.random.default_rng(1)
+    masks = [np.ones(b.n, np.uint8)] + [(rng.random(b.n) < f).astype(np.uint8) for f in (0.5, 0.1)]
+    t = r.base_expectations(b, p, masks=masks)
+    _, _, post = r.realign(b, p, want_posteriors=True)
+    for k, m in enumerate(masks):
+        want = np.zeros((len(b.ref), 5), dtype=np.int64)
+        for i in np.nonzero(m)[0]:
+            s = slice(post["off"][i], post["off"][i + 1])
+            np.add.at(want, (b.ref_start[i] + post["ref_pos"][s].astype(np.int64), np.minimum(b.read(i)[post["read_pos"][s]], 4)),
+                      post["prob_1e7"][s].astype(np.int64))
+        assert np.array_equal(t[k], want), k
+    assert t[0][:, 4].sum() > 0 and t[0][:, :4].sum() > t[1][:, :4].sum() > t[2][:, :4].sum() > 0
+    r.max_cells = int(r.cells // 5)                                     # ~5 library calls
+    assert np.array_equal(r.base_expectations(b, p, masks=masks), t)
+    r.close()
+
+
+def test_margin_align_snp_caller_on_gpu_equals_checker(tmp_path):
+    from nanopore_b200.analyses import marginAlignSnpCaller as masc
+    from test_host_snpcaller import make_snp_experiment
+
+    class Small(masc.MarginAlignSnpCaller):
+        hmmTypes = ("cactus", "trained_40")
+        coverages = (1000000, 2, 1)
+        seed = 3
+    outs = []
+    for tag, factory in (("gpu", None), ("cpu", oracle_realigner_factory())):
+        ref_fa, fq, chained, _, _, _ = make_snp_experiment(str(tmp_path / tag), seed=19)
+        outdir = str(tmp_path / tag / "analysis")
+        os.makedirs(outdir)
+        prev = realign.setRealignerFactory(factory) if factory else None
+        try:
+            assert Stack(Small(fq, "2D", ref_fa, chained, outdir)).startJobTree(None) == 0
+        finally:
+            if factory:
+                realign.setRealignerFactory(prev)
+        outs.append(os.path.join(outdir, "marginaliseConsensus.xml"))
+    assert filecmp.cmp(outs[0], outs[1], shallow=False)

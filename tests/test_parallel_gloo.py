@@ -65,6 +65,9 @@ def test_world_size_2_matches_single_rank(tmp_path):
     assert len(got["post"]["ref_pos"]) > 0
     st = r.expectations(b, p)
     assert FixedStats(got["hi"], got["lo"]) == st                        # exact: independent of the sharding
+    masks = [np.ones(b.n, np.uint8), np.array([1, 0, 1, 0, 0, 1, 0], np.uint8)]
+    t = r.base_expectations(b, p, masks=masks)                           # per-position base expectations: int64 all-reduce
+    assert np.array_equal(np.array(got["tables"], dtype=np.int64), t) and t[1].sum() > 0 and t[0].sum() > t[1].sum()
     r.set_hmm(Hmm.loadHmm(os.path.join(HERE, "golden", "blasr_hmm_0.txt")))
     ops2, off2, _ = r.realign(b, p)
     assert got["ops_trained"] == ops2.tolist() and got["off_trained"] == off2.tolist()
