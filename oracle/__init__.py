@@ -78,6 +78,8 @@ def lib():
                                        C.c_void_p, C.c_void_p, C.POINTER(_Params), C.c_void_p, C.c_int64, C.c_void_p,
                                        C.POINTER(C.c_int64)]
         L.po_set_exact_logadd.argtypes = [C.c_int]
+        L.po_set_upstream_arithmetic.argtypes = [C.c_int]
+        L.po_get_upstream_arithmetic.restype = C.c_int
         _lib = L
     return _lib
 
@@ -96,6 +98,20 @@ def exp(x):
 
 def set_exact_logadd(on):
     lib().po_set_exact_logadd(int(bool(on)))
+
+
+UP_UNFUSED_HORNER, UP_LIBM_EXP, UP_GREEDY_ORDER = 1, 2, 4
+
+
+def set_upstream_arithmetic(flags):
+    """Differential runs only (scripts/differential.py): bit mask of UP_* that replaces the documented deviations of the
+    oracle (header of phmm_oracle.c, items 1-3) by the recalled upstream behaviour.  0 = the arithmetic the CUDA library
+    implements."""
+    lib().po_set_upstream_arithmetic(int(flags))
+
+
+def get_upstream_arithmetic():
+    return int(lib().po_get_upstream_arithmetic())
 
 
 def make_params(expansion=10, trim=14, split_side=3000, gap_gamma=0.5, match_gamma=0.0,

@@ -38,6 +38,12 @@
  *       64-bit fixed point (units of 2^-32) so that sums are independent of
  *       evaluation order (upstream adds doubles).
  *
+ * Each of (1)-(3) has a switch (po_set_upstream_arithmetic, bits PO_UP_*) that
+ * replaces it by the recalled upstream behaviour, so that a differential run
+ * against a real cactus_realign binary (scripts/differential.py) can tell which
+ * deviation a mismatch comes from.  The CUDA library implements the default
+ * (switches off) arithmetic only.
+ *
  * States (utils.py:617): 0 match, 1 shortGapX, 2 shortGapY,
  * 3 longGapX, 4 longGapY.  X = cigar target = reference, Y = read.
  * Symbols: A=0 C=1 G=2 T=3, anything else 4 (N).
@@ -69,8 +75,29 @@ static int g_exact_logadd = 0; /* tests only: replace the cubic by log1p(exp()) 
 
 void po_set_exact_logadd(int on) { g_exact_logadd = on; }
 
+/* Differential runs only: undo the documented deviations one by one. */
+#define PO_UP_UNFUSED_HORNER 1 /* (1) product and sum of every Horner step rounded separately (x86-64 gcc without -mfma) */
+#define PO_UP_LIBM_EXP 2       /* (2) libm exp() for posterior and expectation probabilities */
+#define PO_UP_GREEDY_ORDER 4   /* (3) pairs made ordered greedily by descending weight instead of by the exact chain DP */
+static int g_upstream = 0;
+
+void po_set_upstream_arithmetic(int flags) { g_upstream = flags; }
+int po_get_upstream_arithmetic(void) { return g_upstream; }
+
+/* this file is compiled with -ffp-contract=off: a * b + c below is two roundings */
+static inline double po_lookup_unfused(double x) {
+    if (x <= 1.00)
+        return ((-0.009350833524763 * x + 0.130659527668286) * x + 0.498799810682272) * x + 0.693203116424741;
+    if (x <= 2.50)
+        return ((-0.014532321752540 * x + 0.139942324101744) * x + 0.495635523139337) * x + 0.692140569840976;
+    if (x <= 4.50)
+        return ((-0.004605031767994 * x + 0.063427417320019) * x + 0.695956496475118) * x + 0.514272634594009;
+    return ((-0.000458661602210 * x + 0.009695946122598) * x + 0.930734667215156) * x + 0.168037164329057;
+}
+
 static inline double po_lookup(double x) {
     /* piecewise cubic fit of log(1+exp(-x))+x ... i.e. log(exp(x)+1), x in [0,7.5) */
+    if (g_upstream & PO_UP_UNFUSED_HORNER) return po_lookup_unfused(x);
     if (x <= 1.00)
         return fma(fma(fma(-0.009350833524763, x, 0.130659527668286), x, 0.498799810682272), x, 0.693203116424741);
     if (x <= 2.50)
@@ -94,6 +121,7 @@ double po_logadd(double x, double y) {
 /* exp() built only from IEEE primitives (fma, add, integer ops): identical
  * instruction-for-instruction in the CUDA kernels.  |rel err| < 2 ulp. */
 double po_exp(double x) {
+    if (g_upstream & PO_UP_LIBM_EXP) return exp(x);
     if (!(x > -700.0)) return 0.0;         /* also catches NaN, -inf */
     if (x > 700.0) return INFINITY;
     const double SHIFT = 6755399441055744.0; /* 1.5 * 2^52 */
@@ -617,6 +645,50 @@ static int64_t mea_region(const diag_t *band, int64_t lX, int64_t lY, const pair
     return score;
 }
 
+/* Recalled upstream scheme for "make the pairs ordered" (filterPairwiseAlignmentToMakePairsOrdered over a poset
+ * alignment): take the usable pairs (wr > 0) of the whole read by descending reweighted weight (ties: smaller x, then
+ * smaller y) and keep a pair when it is consistent with every pair kept so far, i.e. its neighbours in x among the kept
+ * pairs lie strictly below / above it in both coordinates.  Appends the kept pair indices in ascending x to chain.
+ * PO_UP_GREEDY_ORDER only. */
+typedef struct { const int64_t *wr; const pairs_t *p; } greedy_ctx;
+static int cmp_greedy(const void *a, const void *b, void *ctx) {
+    const greedy_ctx *g = (const greedy_ctx *)ctx;
+    int64_t i = *(const int64_t *)a, j = *(const int64_t *)b;
+    if (g->wr[i] != g->wr[j]) return g->wr[i] > g->wr[j] ? -1 : 1;
+    if (g->p->x[i] != g->p->x[j]) return g->p->x[i] < g->p->x[j] ? -1 : 1;
+    if (g->p->y[i] != g->p->y[j]) return g->p->y[i] < g->p->y[j] ? -1 : 1;
+    return 0;
+}
+static int64_t greedy_order(const pairs_t *p, const int64_t *wr, int64_t lX, vec64 *chain) {
+    int64_t n = 0, score = 0;
+    int64_t *idx = (int64_t *)malloc(sizeof(int64_t) * (size_t)(p->n + 1));
+    for (int64_t i = 0; i < p->n; i++) if (wr[i] > 0) idx[n++] = i;
+    greedy_ctx g = { wr, p };
+    qsort_r(idx, (size_t)n, sizeof(int64_t), cmp_greedy, &g);
+    /* kept pair (index + 1) at each x, and a bit tree over x for neighbour queries */
+    int64_t size = 1; while (size < lX + 1) size <<= 1;
+    int64_t *at = (int64_t *)calloc((size_t)(lX + 1), sizeof(int64_t));
+    unsigned char *tree = (unsigned char *)calloc((size_t)(2 * size), 1);
+    for (int64_t k = 0; k < n; k++) {
+        int64_t i = idx[k], x = p->x[i], y = p->y[i];
+        if (at[x]) continue;
+        /* predecessor: rightmost kept x' < x */
+        int64_t pre = -1, suc = -1, node;
+        for (node = x + size; node > 1; node >>= 1)
+            if ((node & 1) && tree[node - 1]) { node = node - 1; while (node < size) node = tree[2 * node + 1] ? 2 * node + 1 : 2 * node; pre = node - size; break; }
+        for (node = x + size; node > 1; node >>= 1)
+            if (!(node & 1) && tree[node + 1]) { node = node + 1; while (node < size) node = tree[2 * node] ? 2 * node : 2 * node + 1; suc = node - size; break; }
+        if (pre >= 0 && p->y[at[pre] - 1] >= y) continue;
+        if (suc >= 0 && p->y[at[suc] - 1] <= y) continue;
+        at[x] = i + 1;
+        for (node = x + size; node >= 1; node >>= 1) tree[node] = 1;
+        score += wr[i];
+    }
+    for (int64_t x = 0; x <= lX; x++) if (at[x]) v_push(chain, at[x] - 1);
+    free(idx); free(at); free(tree);
+    return score;
+}
+
 /* convertAlignedPairsToPairwiseAlignment: D (reference-only) before I between
  * matched pairs; ops as (len<<2)|code.  Returns number of ops. */
 static int64_t pairs_to_ops(const int64_t *cx, const int64_t *cy, int64_t n, int64_t lX, int64_t lY, vec64 *ops) {
@@ -689,7 +761,8 @@ po_result *po_realign(const po_model *m, const uint8_t *X, int64_t lX, const uin
     }
     /* MEA per region */
     vec64 chain = {0, 0, NULL};
-    for (int64_t i = 0; i < nr; i++) {
+    if (g_upstream & PO_UP_GREEDY_ORDER) res->mea_score = greedy_order(&all, wr, lX, &chain);
+    for (int64_t i = 0; i < nr && !(g_upstream & PO_UP_GREEDY_ORDER); i++) {
         int64_t np = rstart[i + 1] - rstart[i];
         int64_t lx = reg[i].x2 - reg[i].x1, ly = reg[i].y2 - reg[i].y1;
         if (lx + ly == 0) continue;
