@@ -231,6 +231,7 @@ class ShardedRealigner:
         assert dist.get_rank() == 0, "ShardedRealigner lives on rank 0; other ranks run worker_loop()"
         self._rl = _RankLocal(local_factory or _default_local_factory)
         self.cells = 0
+        self.rank_cells = []
         self._sent = None              # (batch, cost parameters, shards) of the batch the ranks hold
         self.set_hmm(hmm)
 
@@ -274,7 +275,8 @@ class ShardedRealigner:
         res = [self._rl.realign(params, want_posteriors)]
         for r in range(1, dist.get_world_size()):
             res.append(_unpack(_recv_blob(r)))                      # only rank 0 receives; nothing is padded or widened
-        self.cells = int(sum(int(x[2][0]) for x in res))
+        self.rank_cells = [int(x[2][0]) for x in res]            # DP cells per rank: the balance of the shards
+        self.cells = int(sum(self.rank_cells))
         ops, off = _concat_ranges([x[0] for x in res], [x[1] for x in res], shards, batch.n, np.uint32)
         post = None
         if want_posteriors:

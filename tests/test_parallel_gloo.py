@@ -102,3 +102,23 @@ def test_command_line_under_two_ranks_writes_the_single_process_sam(tmp_path):
     finally:
         realign.setRealignerFactory(prev)
     assert filecmp.cmp(out1, out2, shallow=False)
+
+
+def test_baseline_configs_script_dry_run_on_two_ranks(tmp_path):
+    """scripts/configs_multi_gpu.py (BASELINE.json configs 3, 4, 5 through ShardedRealigner) at toy size over gloo: every
+    config's sample equals the single-rank run, CIGARs span the reads, EM likelihoods rise."""
+    out = str(tmp_path / "configs.json")
+    port = free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_dist_configs_worker.py"), "--scale", "0.00002", "--len-scale", "0.03",
+                                       "--procs", "2", "--verify", "4", "--out", out], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        o, _ = p.communicate(timeout=600)
+        assert p.returncode == 0, o
+    lines = [json.loads(ln) for ln in open(out)]
+    assert [ln["config"] for ln in lines] == [3, 4, 5]
+    assert lines[0]["sample_equals_single_gpu"] and lines[0]["cigars_span_reads"] and len(lines[0]["rank_cells"]) == 2
+    assert lines[1]["sample_statistics_equal_single_gpu"] and lines[1]["monotone"] and len(lines[1]["running_likelihoods"]) == 5
+    assert lines[2]["sample_equals_single_gpu"] and lines[2]["reads"] == 20 and min(lines[2]["rank_cells"]) > 0
