@@ -312,6 +312,15 @@ int64_t budget(phmm_ctx *ctx) {
     return (int64_t)(((double)fr + (double)g_held_bytes) * 0.8);
 }
 
+void release_scratch(phmm_ctx *ctx) {
+    DevBuf *all[] = {&ctx->d_fring, &ctx->d_dtab, &ctx->d_bring, &ctx->d_dots, &ctx->d_ring, &ctx->d_wide, &ctx->d_fsave, &ctx->d_totals,
+                     &ctx->d_recs, &ctx->d_recoff, &ctx->d_cand, &ctx->d_px, &ctx->d_py, &ctx->d_pw, &ctx->d_npairs, &ctx->d_expT, &ctx->d_expE,
+                     &ctx->d_expLL, &ctx->d_sumx, &ctx->d_sumy, &ctx->d_dstart, &ctx->d_dfill, &ctx->d_sidx, &ctx->d_wre, &ctx->d_pred,
+                     &ctx->d_colmap, &ctx->d_sring, &ctx->d_lring, &ctx->d_mrx, &ctx->d_mry, &ctx->d_mrn, &ctx->d_nmruns, &ctx->d_score,
+                     &ctx->d_cx, &ctx->d_cy, &ctx->d_cn, &ctx->d_coff};
+    for (DevBuf *d : all) d->release();
+}
+
 // Sizes scratch and (re)allocates it.  pair capacities scale with pair_factor.
 int plan_memory(phmm_ctx *ctx) {
     BatchState &b = ctx->b;
@@ -392,47 +401,62 @@ int plan_memory(phmm_ctx *ctx) {
     b.fb_slots = (int)want; b.dec_slots = (int)dec_want;
     b.stats.slot_bytes = slot_bytes; b.stats.n_slots = want;
 
-    if (b.fast) {
-        ctx->d_fring.release(); ctx->d_bring.release(); ctx->d_dots.release(); ctx->d_dtab.release();
-        CK(ctx->d_recs.ensure((size_t)b.rec_off[nreg] * sizeof(DiagRec) + 64));
-        CK(ctx->d_recoff.ensure((size_t)(nreg + 1) * 8));
-        CK(ctx->d_ring.ensure((size_t)want * b.ring_doubles * 8));
-        CK(ctx->d_wide.ensure((size_t)want * 4 * NS * b.wg * 8));
-        CK(ctx->d_fsave.ensure((size_t)want * 2 * CS * b.wcap * 8));
-        CK(ctx->d_totals.ensure((size_t)want * ((size_t)b.tcap + b.wg) * 8));
-        b.ccap = b.expect ? 1 : (ctx->opt_ccap > 0 ? ctx->opt_ccap : 2 * b.max_pairs + 1024);
-        CK(ctx->d_cand.ensure((size_t)want * (size_t)b.ccap * 8));
-    } else {
-        ctx->d_ring.release(); ctx->d_wide.release(); ctx->d_recs.release();
-        CK(ctx->d_dtab.ensure((size_t)want * b.dcap * sizeof(DiagRec)));
-        CK(ctx->d_fring.ensure((size_t)want * b.ring_cells * NS * 8));
-        CK(ctx->d_bring.ensure((size_t)want * 3 * b.bw * NS * 8));
-        CK(ctx->d_dots.ensure((size_t)want * 2 * b.bw * 8));
-    }
-    CK(ctx->d_px.ensure((size_t)b.total_pair_cap * 4 + 16));
-    CK(ctx->d_py.ensure((size_t)b.total_pair_cap * 4 + 16));
-    CK(ctx->d_pw.ensure((size_t)b.total_pair_cap * 4 + 16));
-    CK(ctx->d_npairs.ensure((size_t)nreg * 4 + 16));
-    if (b.expect) {
-        CK(ctx->d_expT.ensure((size_t)nreg * 25 * 8));
-        CK(ctx->d_expE.ensure((size_t)nreg * 80 * 8));
-        CK(ctx->d_expLL.ensure((size_t)nreg * 8));
-    } else {
-        CK(ctx->d_sumx.ensure((size_t)dec_want * (b.max_lx + 1) * 4));
-        CK(ctx->d_sumy.ensure((size_t)dec_want * (b.max_ly + 1) * 4));
-        CK(ctx->d_dstart.ensure((size_t)dec_want * (b.max_nd + 4) * 4));
-        CK(ctx->d_dfill.ensure((size_t)dec_want * (b.max_nd + 4) * 4));
-        CK(ctx->d_sidx.ensure((size_t)dec_want * (b.max_pairs + 1) * 4));
-        CK(ctx->d_wre.ensure((size_t)dec_want * (b.max_pairs + 1) * 8));
-        CK(ctx->d_pred.ensure((size_t)dec_want * (b.max_pairs + 1) * 4));
-        CK(ctx->d_colmap.ensure((size_t)dec_want * 2 * (b.max_lx + 2) * 8));
-        CK(ctx->d_sring.ensure((size_t)dec_want * 4 * b.bw * 8));
-        CK(ctx->d_lring.ensure((size_t)dec_want * 4 * b.bw * 4));
-        CK(ctx->d_mrx.ensure((size_t)b.total_mrun_cap * 4 + 16));
-        CK(ctx->d_mry.ensure((size_t)b.total_mrun_cap * 4 + 16));
-        CK(ctx->d_mrn.ensure((size_t)b.total_mrun_cap * 4 + 16));
-        CK(ctx->d_nmruns.ensure((size_t)nreg * 4 + 16));
-        CK(ctx->d_score.ensure((size_t)nreg * 8 + 16));
+    // Scratch of an earlier batch that is larger than this plan needs stays allocated (DevBuf only grows), so the sum can
+    // exceed the budget when consecutive batches differ a lot (mixed read lengths): on the first failed allocation every
+    // scratch buffer is released and the plan is allocated afresh.
+    auto alloc_all = [&]() -> cudaError_t {
+#define TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { (void)cudaGetLastError(); return e_; } } while (0)
+        if (b.fast) {
+            ctx->d_fring.release(); ctx->d_bring.release(); ctx->d_dots.release(); ctx->d_dtab.release();
+            TRY(ctx->d_recs.ensure((size_t)b.rec_off[nreg] * sizeof(DiagRec) + 64));
+            TRY(ctx->d_recoff.ensure((size_t)(nreg + 1) * 8));
+            TRY(ctx->d_ring.ensure((size_t)want * b.ring_doubles * 8));
+            TRY(ctx->d_wide.ensure((size_t)want * 4 * NS * b.wg * 8));
+            TRY(ctx->d_fsave.ensure((size_t)want * 2 * CS * b.wcap * 8));
+            TRY(ctx->d_totals.ensure((size_t)want * ((size_t)b.tcap + b.wg) * 8));
+            b.ccap = b.expect ? 1 : (ctx->opt_ccap > 0 ? ctx->opt_ccap : 2 * b.max_pairs + 1024);
+            TRY(ctx->d_cand.ensure((size_t)want * (size_t)b.ccap * 8));
+        } else {
+            ctx->d_ring.release(); ctx->d_wide.release(); ctx->d_recs.release();
+            TRY(ctx->d_dtab.ensure((size_t)want * b.dcap * sizeof(DiagRec)));
+            TRY(ctx->d_fring.ensure((size_t)want * b.ring_cells * NS * 8));
+            TRY(ctx->d_bring.ensure((size_t)want * 3 * b.bw * NS * 8));
+            TRY(ctx->d_dots.ensure((size_t)want * 2 * b.bw * 8));
+        }
+        TRY(ctx->d_px.ensure((size_t)b.total_pair_cap * 4 + 16));
+        TRY(ctx->d_py.ensure((size_t)b.total_pair_cap * 4 + 16));
+        TRY(ctx->d_pw.ensure((size_t)b.total_pair_cap * 4 + 16));
+        TRY(ctx->d_npairs.ensure((size_t)nreg * 4 + 16));
+        if (b.expect) {
+            TRY(ctx->d_expT.ensure((size_t)nreg * 25 * 8));
+            TRY(ctx->d_expE.ensure((size_t)nreg * 80 * 8));
+            TRY(ctx->d_expLL.ensure((size_t)nreg * 8));
+        } else {
+            TRY(ctx->d_sumx.ensure((size_t)dec_want * (b.max_lx + 1) * 4));
+            TRY(ctx->d_sumy.ensure((size_t)dec_want * (b.max_ly + 1) * 4));
+            TRY(ctx->d_dstart.ensure((size_t)dec_want * (b.max_nd + 4) * 4));
+            TRY(ctx->d_dfill.ensure((size_t)dec_want * (b.max_nd + 4) * 4));
+            TRY(ctx->d_sidx.ensure((size_t)dec_want * (b.max_pairs + 1) * 4));
+            TRY(ctx->d_wre.ensure((size_t)dec_want * (b.max_pairs + 1) * 8));
+            TRY(ctx->d_pred.ensure((size_t)dec_want * (b.max_pairs + 1) * 4));
+            TRY(ctx->d_colmap.ensure((size_t)dec_want * 2 * (b.max_lx + 2) * 8));
+            TRY(ctx->d_sring.ensure((size_t)dec_want * 4 * b.bw * 8));
+            TRY(ctx->d_lring.ensure((size_t)dec_want * 4 * b.bw * 4));
+            TRY(ctx->d_mrx.ensure((size_t)b.total_mrun_cap * 4 + 16));
+            TRY(ctx->d_mry.ensure((size_t)b.total_mrun_cap * 4 + 16));
+            TRY(ctx->d_mrn.ensure((size_t)b.total_mrun_cap * 4 + 16));
+            TRY(ctx->d_nmruns.ensure((size_t)nreg * 4 + 16));
+            TRY(ctx->d_score.ensure((size_t)nreg * 8 + 16));
+        }
+        return cudaSuccess;
+#undef TRY
+    };
+    if (alloc_all() != cudaSuccess) {
+        release_scratch(ctx);
+        b.ccap = 1;
+        cudaError_t e2 = alloc_all();
+        if (e2 != cudaSuccess)
+            return fail(ctx, e2 == cudaErrorMemoryAllocation ? PHMM_E_NOMEM : PHMM_E_CUDA, std::string("scratch allocation: ") + cudaGetErrorString(e2));
     }
     // regions carry the plan (pair_off, caps): upload
     CK(cudaMemcpyAsync(ctx->d_regions.p, b.regions.data(), nreg * sizeof(Region), cudaMemcpyHostToDevice, ctx->stream));

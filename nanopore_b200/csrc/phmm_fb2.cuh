@@ -127,6 +127,45 @@ __device__ __forceinline__ double logadd_t(double x, double y, const char *ctab)
 #endif
 }
 
+// The same coefficient rows in constant memory (tuning variants: the shared-memory pipe is the busiest unit of k_fb2 --
+// 9.5 wavefronts per cell, half of them these rows -- and the constant cache is a different path).
+__constant__ double c_logadd[16] = {
+    -0.009350833524763, 0.130659527668286, 0.498799810682272, 0.693203116424741,
+    -0.014532321752540, 0.139942324101744, 0.495635523139337, 0.692140569840976,
+    -0.004605031767994, 0.063427417320019, 0.695956496475118, 0.514272634594009,
+    -0.000458661602210, 0.009695946122598, 0.930734667215156, 0.168037164329057};
+
+__device__ __forceinline__ double logadd_k(double x, double y) {
+    const double d = x - y;
+    const int dh = __double2hiint(d);
+    const bool lt = dh < 0;
+    const double mn = lt ? x : y, mx = lt ? y : x;
+    const double t = fabs(d);
+    int off = 0;
+    if (t > 1.0) off = 4;
+    if (t > 2.5) off = 8;
+    if (t > 4.5) off = 12;
+    const double r = fma(fma(fma(c_logadd[off], t, c_logadd[off + 1]), t, c_logadd[off + 2]), t, c_logadd[off + 3]) + mn;
+    return (t < 7.5) ? r : mx;
+}
+
+#ifndef PHMM_COEF_CONST
+#define PHMM_COEF_CONST 0       // 0: rows from shared memory; 1: all from constant memory; 2: the match-state chains only
+#endif
+#if PHMM_COEF_CONST == 1
+#define LA_M(x, y, ctab) logadd_k(x, y)
+#define LA_G(x, y, ctab) logadd_k(x, y)
+#elif PHMM_COEF_CONST == 2
+#define LA_M(x, y, ctab) logadd_k(x, y)
+#define LA_G(x, y, ctab) logadd_t(x, y, ctab)
+#else
+#define LA_M(x, y, ctab) logadd_t(x, y, ctab)
+#define LA_G(x, y, ctab) logadd_t(x, y, ctab)
+#endif
+#ifndef PHMM_TAB_SUM
+#define PHMM_TAB_SUM 0          // 1: shared memory holds the emissions only; (emission + transition) is added per cell, the
+#endif                          //    transition coming from the kernel parameters (constant bank operand of the DADD)
+
 // Shared-memory tables of (emission + transition) sums, one padded row of CS doubles per symbol (pair); the
 // scalar definition adds `from + (eP + tP)`, so the parenthesised sum can be taken once per model.
 //   tM[cX*5+cY][s] = eM[cX][cY] + tr[s -> M]                              s = M, sX, sY, lX, lY
@@ -137,6 +176,7 @@ struct Tabs {
     const double *tM, *tX, *tY;
     const char *ctab;
 };
+constexpr int TROW = PHMM_TAB_SUM ? 1 : TS;   // doubles per table row
 
 // One column of 5 state values.  GUARD: scalar loads through an in-band test (any buffer, any stride);
 // otherwise unguarded loads (16-byte ones when the columns are padded, CS = 6) from a CS-strided shared-memory column whose out-of-band
@@ -173,53 +213,73 @@ __device__ __forceinline__ void st_col(double *p, const double o[NS]) {
 
 // Rows of the (emission + transition) tables, loaded as 16-byte pairs.
 struct GapRow { double s, ss, l, ll, sw; };    // M->short, short->short, M->long, long->long, other short->short (switch)
-template <bool SWITCH>
-__device__ __forceinline__ GapRow ld_gap(const double *r) {
+struct MatRow { double m, sx, sy, lx, ly; };   // s -> M for s = M, sX, sY, lX, lY
+#if PHMM_TAB_SUM
+template <bool SWITCH, bool ISX>
+__device__ __forceinline__ GapRow ld_gap(const double *r, const DevModel &m) {
+    const double e = r[0];
+    constexpr int S = ISX ? S_SX : S_SY, L = ISX ? S_LX : S_LY, O = ISX ? S_SY : S_SX;
+    GapRow g;
+    g.s = e + m.tr[S_M * 5 + S]; g.ss = e + m.tr[S * 5 + S]; g.l = e + m.tr[S_M * 5 + L]; g.ll = e + m.tr[L * 5 + L];
+    g.sw = SWITCH ? e + m.tr[O * 5 + S] : 0.0;
+    return g;
+}
+__device__ __forceinline__ MatRow ld_mat(const double *r, const DevModel &m) {
+    const double e = r[0];
+    MatRow q;
+    q.m = e + m.tr[S_M * 5 + S_M]; q.sx = e + m.tr[S_SX * 5 + S_M]; q.sy = e + m.tr[S_SY * 5 + S_M];
+    q.lx = e + m.tr[S_LX * 5 + S_M]; q.ly = e + m.tr[S_LY * 5 + S_M];
+    return q;
+}
+#else
+// Rows of the (emission + transition) tables, loaded as 16-byte pairs.
+template <bool SWITCH, bool ISX>
+__device__ __forceinline__ GapRow ld_gap(const double *r, const DevModel &) {
     const double2 a = *reinterpret_cast<const double2 *>(r + TG_S);
     const double2 b = *reinterpret_cast<const double2 *>(r + TG_L);
     GapRow g; g.s = a.x; g.ss = a.y; g.l = b.x; g.ll = b.y; g.sw = SWITCH ? r[TG_SW] : 0.0;
     return g;
 }
-struct MatRow { double m, sx, sy, lx, ly; };   // s -> M for s = M, sX, sY, lX, lY
-__device__ __forceinline__ MatRow ld_mat(const double *r) {
+__device__ __forceinline__ MatRow ld_mat(const double *r, const DevModel &) {
     const double2 a = *reinterpret_cast<const double2 *>(r);
     const double2 b = *reinterpret_cast<const double2 *>(r + 2);
     MatRow m; m.m = a.x; m.sx = a.y; m.sy = b.x; m.lx = b.y; m.ly = r[4];
     return m;
 }
+#endif
 
 // Forward cell from register values.  L = lower (x-1,y), U = upper (x,y-1) on diagonal d-1, C = middle (x-1,y-1)
 // on d-2.  Transition order of SURVEY.md A.4.
 template <bool SWITCH>
-__device__ __forceinline__ void fwd_cell_r(const Tabs &t, int cX, int cY, double LM, double LsX, double LsY, double LlX,
+__device__ __forceinline__ void fwd_cell_r(const Tabs &t, const DevModel &md, int cX, int cY, double LM, double LsX, double LsY, double LlX,
                                            const ColV &C, double UM, double UsX, double UsY, double UlY, double out[NS]) {
     const char *ctab = t.ctab;
-    const GapRow gx = ld_gap<SWITCH>(t.tX + cX * TS), gy = ld_gap<SWITCH>(t.tY + cY * TS);
-    const MatRow gm = ld_mat(t.tM + (cX * 5 + cY) * TS);
+    const GapRow gx = ld_gap<SWITCH, true>(t.tX + cX * TROW, md), gy = ld_gap<SWITCH, false>(t.tY + cY * TROW, md);
+    const MatRow gm = ld_mat(t.tM + (cX * 5 + cY) * TROW, md);
     {
         double a = LM + gx.s;
-        a = logadd_t(a, LsX + gx.ss, ctab);
-        if (SWITCH) a = logadd_t(a, LsY + gx.sw, ctab);
+        a = LA_G(a, LsX + gx.ss, ctab);
+        if (SWITCH) a = LA_G(a, LsY + gx.sw, ctab);
         out[S_SX] = a;
         double b = LM + gx.l;
-        b = logadd_t(b, LlX + gx.ll, ctab);
+        b = LA_G(b, LlX + gx.ll, ctab);
         out[S_LX] = b;
     }
     {
         double a = C.M + gm.m;
-        a = logadd_t(a, C.sX + gm.sx, ctab);
-        a = logadd_t(a, C.sY + gm.sy, ctab);
-        a = logadd_t(a, C.lX + gm.lx, ctab);
-        a = logadd_t(a, C.lY + gm.ly, ctab);
+        a = LA_M(a, C.sX + gm.sx, ctab);
+        a = LA_M(a, C.sY + gm.sy, ctab);
+        a = LA_M(a, C.lX + gm.lx, ctab);
+        a = LA_M(a, C.lY + gm.ly, ctab);
         out[S_M] = a;
     }
     {
         double a = UM + gy.s;
-        a = logadd_t(a, UsY + gy.ss, ctab);
-        if (SWITCH) a = logadd_t(a, UsX + gy.sw, ctab);
+        a = LA_G(a, UsY + gy.ss, ctab);
+        if (SWITCH) a = LA_G(a, UsX + gy.sw, ctab);
         out[S_SY] = a;
         double b = UM + gy.l;
-        b = logadd_t(b, UlY + gy.ll, ctab);
+        b = LA_G(b, UlY + gy.ll, ctab);
         out[S_LY] = b;
     }
 }
@@ -227,39 +287,39 @@ __device__ __forceinline__ void fwd_cell_r(const Tabs &t, int cX, int cY, double
 // Backward cell from register values: Bm = B_M of (x+1,y+1) on d+2; BsY, BlY of (x,y+1) and BsX, BlX of (x+1,y) on d+1.
 // cXn = X[x], cYn = Y[y]: the symbols those steps consume.
 template <bool SWITCH>
-__device__ __forceinline__ void bwd_cell_r(const Tabs &t, int cXn, int cYn, double Bm, double BsX, double BlX, double BsY,
+__device__ __forceinline__ void bwd_cell_r(const Tabs &t, const DevModel &md, int cXn, int cYn, double Bm, double BsX, double BlX, double BsY,
                                            double BlY, double out[NS]) {
     const char *ctab = t.ctab;
-    const GapRow gx = ld_gap<SWITCH>(t.tX + cXn * TS), gy = ld_gap<SWITCH>(t.tY + cYn * TS);
-    const MatRow gm = ld_mat(t.tM + (cXn * 5 + cYn) * TS);
+    const GapRow gx = ld_gap<SWITCH, true>(t.tX + cXn * TROW, md), gy = ld_gap<SWITCH, false>(t.tY + cYn * TROW, md);
+    const MatRow gm = ld_mat(t.tM + (cXn * 5 + cYn) * TROW, md);
     {
         double a = Bm + gm.m;
-        a = logadd_t(a, BsY + gy.s, ctab);
-        a = logadd_t(a, BlY + gy.l, ctab);
-        a = logadd_t(a, BsX + gx.s, ctab);
-        a = logadd_t(a, BlX + gx.l, ctab);
+        a = LA_M(a, BsY + gy.s, ctab);
+        a = LA_M(a, BlY + gy.l, ctab);
+        a = LA_M(a, BsX + gx.s, ctab);
+        a = LA_M(a, BlX + gx.l, ctab);
         out[S_M] = a;
     }
     {
         double a = Bm + gm.sx;
-        if (SWITCH) a = logadd_t(a, BsY + gy.sw, ctab);
-        a = logadd_t(a, BsX + gx.ss, ctab);
+        if (SWITCH) a = LA_G(a, BsY + gy.sw, ctab);
+        a = LA_G(a, BsX + gx.ss, ctab);
         out[S_SX] = a;
     }
     {
         double a = Bm + gm.sy;
-        a = logadd_t(a, BsY + gy.ss, ctab);
-        if (SWITCH) a = logadd_t(a, BsX + gx.sw, ctab);
+        a = LA_G(a, BsY + gy.ss, ctab);
+        if (SWITCH) a = LA_G(a, BsX + gx.sw, ctab);
         out[S_SY] = a;
     }
     {
         double a = Bm + gm.lx;
-        a = logadd_t(a, BlX + gx.ll, ctab);
+        a = LA_G(a, BlX + gx.ll, ctab);
         out[S_LX] = a;
     }
     {
         double a = Bm + gm.ly;
-        a = logadd_t(a, BlY + gy.ll, ctab);
+        a = LA_G(a, BlY + gy.ll, ctab);
         out[S_LY] = a;
     }
 }
@@ -267,21 +327,21 @@ __device__ __forceinline__ void bwd_cell_r(const Tabs &t, int cXn, int cYn, doub
 // Forward cell from its three predecessor columns: lower = (x-1,y), upper = (x,y-1) on diagonal d-1,
 // middle = (x-1,y-1) on d-2.
 template <bool SWITCH, bool GUARD>
-__device__ __forceinline__ void fwd_cell3(const Tabs &t, const double *pl, bool okl, const double *pu, bool oku,
+__device__ __forceinline__ void fwd_cell3(const Tabs &t, const DevModel &md, const double *pl, bool okl, const double *pu, bool oku,
                                           const double *pm, bool okm, int cX, int cY, double out[NS]) {
     const ColV L = ld_col<GUARD>(pl, okl), C = ld_col<GUARD>(pm, okm), U = ld_col<GUARD>(pu, oku);
-    fwd_cell_r<SWITCH>(t, cX, cY, L.M, L.sX, L.sY, L.lX, C, U.M, U.sX, U.sY, U.lY, out);
+    fwd_cell_r<SWITCH>(t, md, cX, cY, L.M, L.sX, L.sY, L.lX, C, U.M, U.sX, U.sY, U.lY, out);
 }
 
 // Backward cell from its three successor columns: pu = (x, y+1), pl = (x+1, y) on diagonal d+1,
 // pm = (x+1, y+1) on d+2.
 template <bool SWITCH, bool GUARD>
-__device__ __forceinline__ void bwd_cell3(const Tabs &t, const double *pl, bool okl, const double *pu, bool oku,
+__device__ __forceinline__ void bwd_cell3(const Tabs &t, const DevModel &md, const double *pl, bool okl, const double *pu, bool oku,
                                           const double *pm, bool okm, int cXn, int cYn, double out[NS]) {
     const double Bm = (!GUARD || okm) ? pm[S_M] : PHMM_NEG_INF;
     const double BsY = (!GUARD || oku) ? pu[S_SY] : PHMM_NEG_INF, BlY = (!GUARD || oku) ? pu[S_LY] : PHMM_NEG_INF;
     const double BsX = (!GUARD || okl) ? pl[S_SX] : PHMM_NEG_INF, BlX = (!GUARD || okl) ? pl[S_LX] : PHMM_NEG_INF;
-    bwd_cell_r<SWITCH>(t, cXn, cYn, Bm, BsX, BlX, BsY, BlY, out);
+    bwd_cell_r<SWITCH>(t, md, cXn, cYn, Bm, BsX, BlX, BsY, BlY, out);
 }
 
 // left-to-right logAdd fold of n values produced by f(i), starting from -inf (dpDiagonal_dotProduct order)
@@ -342,7 +402,14 @@ __global__ void k_records(const Region *regions, const Run *runs, int n_regions,
         const int wf = w > wcap ? REC_WIDE : 0;
         int lo = min(clo, c1lo), hi = max(chi, c1hi);
         if (c2lo <= c2hi) { lo = min(lo, c2lo); hi = max(hi, c2hi); }
-        const bool fast3 = !(wf | wf1 | wf2) && (hi - lo + 3 <= wcap);
+        // the unguarded loops read, around every cell, columns of the two neighbouring diagonals; only the band of those
+        // diagonals plus ONE sentinel column either side is guaranteed to hold a value or -inf (FB2 sentinels), so every
+        // such read must stay within that reach -- forward into d (from d-1, d-2) and backward into d-2 (from d-1, d)
+        const int dl = (d & 1) ? -1 : 0;
+        const bool have2 = c2lo <= c2hi;
+        const bool fwd_ok = clo + dl >= c1lo - 1 && chi + dl + 1 <= c1hi + 1 && (!have2 || (clo >= c2lo - 1 && chi <= c2hi + 1));
+        const bool bwd_ok = !have2 || (c2lo + dl >= c1lo - 1 && c2hi + dl + 1 <= c1hi + 1 && c2lo >= clo - 1 && c2hi <= chi + 1);
+        const bool fast3 = !(wf | wf1 | wf2) && (hi - lo + 3 <= wcap) && fwd_ok && bwd_ok;
         DiagRec rc; rc.off = off; rc.xlo = xlo; rc.w = w; rc.pad = (tot ? REC_TOT : 0) | wf | (fast3 ? REC_FAST3 : 0);
         out[d] = rc;
         c2lo = c1lo; c2hi = c1hi; wf2 = wf1;
@@ -365,11 +432,12 @@ constexpr int fb2_min_blocks(int nw, bool expect) {
 
 // Shared-memory diagonal buffers.  Cell (d, x) lives in column (x - (d >> 1)) & (wcap - 1) of the buffer of parity
 // d & 1, so a cell overwrites its own `middle` predecessor (d-2, x-1) and its `lower` / `upper` predecessors sit in
-// the same and the adjacent column of the other buffer.  INVARIANT kept for both buffers: every column that is not
-// in the band of the diagonal the buffer currently holds contains -inf.  With it the recurrences read their
-// neighbours without any in-band test, whatever the band does at its ends, as long as the columns of three
-// consecutive diagonals (plus one either side) do not alias modulo wcap (REC_FAST3, decided by k_records).
-// Other diagonals take the guarded path and then restore the invariant by clearing every out-of-band column.
+// the same and the adjacent column of the other buffer.  INVARIANT kept for both buffers: the column either side of
+// the band of the diagonal a buffer holds contains -inf (two sentinel columns, written after the diagonal's cells).
+// With it the recurrences read their neighbours without any in-band test as long as (REC_FAST3, decided by k_records)
+// the columns of three consecutive diagonals plus one either side do not alias modulo wcap and every neighbour read
+// lands inside band +- 1 of the diagonal it reads.  Other diagonals take the guarded path and then clear every
+// out-of-band column of their buffer (a superset of the sentinels).
 // EXPECT (Baum-Welch E-step, replaces `cactus_realign --outputExpectations`): the ring keeps all five forward AND
 // backward values of every cell of the live window (10 doubles per cell, 11 where a total is evaluated), the
 // posterior phase is replaced by an expectation phase over the same diagonals -- every cell independent, no barriers
@@ -409,6 +477,10 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
         sct[8] = -0.004605031767994; sct[9] = 0.063427417320019; sct[10] = 0.695956496475118; sct[11] = 0.514272634594009;
         sct[12] = -0.000458661602210; sct[13] = 0.009695946122598; sct[14] = 0.930734667215156; sct[15] = 0.168037164329057;
     }
+#if PHMM_TAB_SUM
+    for (int i = tid; i < 25; i += NTA) stM[i] = a.m.eM[i];
+    if (tid < 5) { stX[tid] = a.m.eX[tid]; stY[tid] = a.m.eY[tid]; }
+#else
     for (int i = tid; i < 25 * TS; i += NTA) {
         const int r = i / TS, s = i - r * TS;
         stM[i] = s < NS ? a.m.eM[r] + a.m.tr[s * 5 + S_M] : 0.0;
@@ -421,6 +493,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
         stX[tid] = s < NS ? a.m.eX[c] + a.m.tr[fx[s < NS ? s : 0]] : 0.0;
         stY[tid] = s < NS ? a.m.eY[c] + a.m.tr[fy[s < NS ? s : 0]] : 0.0;
     }
+#endif
     Tabs tabs;
     tabs.tM = stM; tabs.tX = stX; tabs.tY = stY; tabs.ctab = reinterpret_cast<const char *>(sct);
     const char *const ctab = tabs.ctab;
@@ -496,13 +569,14 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
             int tk = 0;                                               // upcoming traceback point (all threads)
             int P = tb[0];
             __syncthreads();
+            DiagRec rn = srec[1 & (FB2_RQ - 1)];                       // record of the next diagonal, read one barrier ahead
             for (int d = 1; d <= nd; d++) {
                 if (((d - 1) & (FB2_BATCH - 1)) == 0 && tid < FB2_BATCH) {
                     // records d .. d+31 are in the FIFO; publish d+32 .. d+63 (loaded a batch ago), fetch d+64 .. d+95
                     if (d + FB2_BATCH + tid <= nd) srec[(d + FB2_BATCH + tid) & (FB2_RQ - 1)] = pre;
                     if (d + 2 * FB2_BATCH + tid <= nd) pre = ld_rec(rec + d + 2 * FB2_BATCH + tid);
                 }
-                const DiagRec rc = srec[d & (FB2_RQ - 1)];
+                const DiagRec rc = rn;
                 const int xlo = rc.xlo, w = rc.w;
                 const int h0 = d >> 1, par = d & 1;
                 const int clo = xlo - h0;                             // first column of this diagonal (unwrapped)
@@ -527,7 +601,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                             const double *const pl = b1 + ((c + dl) & cmask) * CS;
                             const double *const pu = b1 + ((c + dl + 1) & cmask) * CS;
                             double o[NS];
-                            fwd_cell3<SWITCH, false>(tabs, pl, true, pu, true, p0, true, cX, cY, o);
+                            fwd_cell3<SWITCH, false>(tabs, a.m, pl, true, pu, true, p0, true, cX, cY, o);
                             st_col<true>(p0, o);
                             if (!FB2_DBG(2)) {
                             rg[i] = o[S_M];
@@ -552,7 +626,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                             const double *const pu = col_ptr(wd1, par ^ 1, 0, x, h1);
                             const double *const pm = col_ptr(wd2, par, 0, x - 1, h2);
                             double o[NS];
-                            fwd_cell3<SWITCH, true>(tabs, pl, okl, pu, oku, pm, okm, cX, cY, o);
+                            fwd_cell3<SWITCH, true>(tabs, a.m, pl, okl, pu, oku, pm, okm, cX, cY, o);
                             st_col<false>(p0, o);
                             rg[i] = o[S_M];
                             if (tot || EXPECT) {
@@ -564,17 +638,17 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                 }
                 {
                     if (fast) {
-                        // columns of diagonal d-2 that left the band: back to -inf (nobody reads them during d)
-                        if (w2 > 0) {
-                            const int clo2 = xlo2 - h0 + 1, chi2 = clo2 + w2 - 1, chi = clo + w - 1;
-                            clear_cols(par, clo2, min(clo - 1, chi2), tid, NC);
-                            clear_cols(par, max(chi + 1, clo2), chi2, tid, NC);
+                        // sentinels: -inf in the column either side of the band (nobody reads them during d)
+                        if (tid < 2 * NS) {
+                            const int side = tid >= NS ? 1 : 0;
+                            sbuf[(par * wcap + ((side ? clo + w : clo - 1) & cmask)) * CS + (tid - side * NS)] = PHMM_NEG_INF;
                         }
                     } else if (!(rc.pad & REC_WIDE)) {
                         // guarded diagonal held in shared memory: restore the invariant for its buffer (the cleared columns
                         // are outside the band, and the only column of this buffer a cell reads is its own)
                         clear_outside(par, clo, w, tid, NC);
                     }
+                    if (d < nd) rn = srec[(d + 1) & (FB2_RQ - 1)];      // published at least one barrier ago; its latency hides in this one
                     __syncthreads();
                 }
                 if (d == P && FB2_DBG(16)) {
@@ -605,12 +679,13 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                     // phase 1: backward sweep
                     {
                         int bxlo1 = 0, bw1 = 0, bf1 = 0, bxlo2 = 0, bw2 = 0, bf2 = 0;      // diagonals dd+1, dd+2
+                        DiagRec rbn = srb[d & (FB2_RQ - 1)];
                         for (int dd = d; dd > traced_to; dd--) {
                             if (((d - dd) & (FB2_BATCH - 1)) == 0 && tid < FB2_BATCH) {
                                 if (dd - FB2_BATCH - tid >= 1) srb[(dd - FB2_BATCH - tid) & (FB2_RQ - 1)] = preb;
                                 if (dd - 2 * FB2_BATCH - tid >= 1) preb = ld_rec(rec + dd - 2 * FB2_BATCH - tid);
                             }
-                            const DiagRec rb = srb[dd & (FB2_RQ - 1)];
+                            const DiagRec rb = rbn;
                             const int hb0 = dd >> 1, bpar = dd & 1;
                             const int bclo = rb.xlo - hb0;
                             // fast: diagonals dd, dd+1, dd+2 are a FAST3 triple (flag of dd+2) and all exist
@@ -632,7 +707,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                                         const double *const pu = b1 + ((c + du) & cmask) * CS;
                                         const double *const pl = b1 + ((c + du + 1) & cmask) * CS;
                                         double o[NS];
-                                        bwd_cell3<SWITCH, false>(tabs, pl, true, pu, true, p0, true, cXn, cYn, o);
+                                        bwd_cell3<SWITCH, false>(tabs, a.m, pl, true, pu, true, p0, true, cXn, cYn, o);
                                         st_col<true>(p0, o);
                                         const double sM = fM + o[S_M];
                                         if (EXPECT) {
@@ -672,7 +747,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                                             const double *const pu = col_ptr(wd1, bpar ^ 1, 2, x, h1);
                                             const double *const pl = col_ptr(wd1, bpar ^ 1, 2, x + 1, h1);
                                             const double *const pm = col_ptr(wd2, bpar, 2, x + 1, h2);
-                                            bwd_cell3<SWITCH, true>(tabs, pl, okl, pu, oku, pm, okm, cXn, cYn, o);
+                                            bwd_cell3<SWITCH, true>(tabs, a.m, pl, okl, pu, oku, pm, okm, cXn, cYn, o);
                                         } else {
 #pragma unroll
                                             for (int s = 0; s < NS; s++) o[s] = endv[s];
@@ -701,12 +776,14 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
                             }
                             {
                                 if (bfast) {
-                                    const int clo2 = bxlo2 - hb0 - 1, chi2 = clo2 + bw2 - 1, chi = bclo + rb.w - 1;
-                                    clear_cols(bpar, clo2, min(bclo - 1, chi2), tid, NC);
-                                    clear_cols(bpar, max(chi + 1, clo2), chi2, tid, NC);
+                                    if (tid < 2 * NS) {
+                                        const int side = tid >= NS ? 1 : 0;
+                                        sbuf[(bpar * wcap + ((side ? bclo + rb.w : bclo - 1) & cmask)) * CS + (tid - side * NS)] = PHMM_NEG_INF;
+                                    }
                                 } else if (!(rb.pad & REC_WIDE)) {
                                     clear_outside(bpar, bclo, rb.w, tid, NC);
                                 }
+                                if (dd - 1 >= 1) rbn = srb[(dd - 1) & (FB2_RQ - 1)];
                                 __syncthreads();
                             }
                             if (!EXPECT && dd == traced_from) {
