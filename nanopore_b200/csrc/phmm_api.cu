@@ -206,6 +206,9 @@ int plan_read(phmm_ctx *ctx, int64_t read, const uint32_t *ops, int64_t nops, in
         else if (code == 2) x += len;
         else return fail(ctx, PHMM_E_ARG, "cigar op code 3 is not M/I/D (read " + std::to_string(read) + ")");
     }
+    // region origins, run offsets and posterior coordinates are int32 (Region::x1/y1, phmm_posteriors::ref_pos)
+    if (lX > 0x7ffffff0 || lY > 0x7ffffff0)
+        return fail(ctx, PHMM_E_ARG, "read " + std::to_string(read) + ": windows longer than 2^31 - 16 bases are not supported");
     if (x != lX || y != lY)
         return fail(ctx, PHMM_E_ARG, "guide cigar of read " + std::to_string(read) + " spans " + std::to_string(x) + "x" +
                                          std::to_string(y) + " but the sequences are " + std::to_string(lX) + "x" + std::to_string(lY));

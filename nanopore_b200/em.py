@@ -165,8 +165,19 @@ def loadAlignments(sequenceFiles, alignmentsFile, maxAlignmentLengthToSample, se
     return batch, len(cigars)
 
 
+def _tie_symmetric(hmm):
+    """fiveState (type 0) is the symmetric model: the X and Y gap states share their parameters.  After normalising,
+    every parameter is averaged with its mirror image under X <-> Y (states sX <-> sY, lX <-> lY; emissions transposed);
+    rows stay normalised because a row and its mirror row both sum to one."""
+    perm = [0, 2, 1, 4, 3]
+    t = np.array(hmm.transitions, dtype=np.float64).reshape(5, 5)
+    hmm.transitions = (0.5 * (t + t[np.ix_(perm, perm)])).reshape(-1).tolist()
+    e = np.array(hmm.emissions, dtype=np.float64).reshape(5, 4, 4)
+    hmm.emissions = (0.5 * (e + e[perm].transpose(0, 2, 1))).reshape(-1).tolist()
+
+
 def mStep(hmm, values, trainEmissions=True, tieEmissions=False):
-    """Expectations (float64[106]) -> next model, in place."""
+    """Expectations (float64[106]) -> next model, in place.  Model type 0 (fiveState) keeps its X / Y symmetry."""
     nxt = Hmm(hmm.type)
     nxt.transitions = [float(v) for v in values[:25]]
     nxt.emissions = [float(v) for v in values[25:105]] if trainEmissions else list(hmm.emissions)
@@ -177,6 +188,11 @@ def mStep(hmm, values, trainEmissions=True, tieEmissions=False):
         nxt.emissions = keep
     elif tieEmissions:
         _tie_emissions(nxt)
+    if nxt.type == 0:
+        keep = list(nxt.emissions)
+        _tie_symmetric(nxt)
+        if not trainEmissions:
+            nxt.emissions = keep
     hmm.transitions, hmm.emissions, hmm.likelihood = nxt.transitions, nxt.emissions, nxt.likelihood
 
 
@@ -220,6 +236,8 @@ def expectationMaximisationTrials(target, sequences, alignments, outputModel, op
     """options.trials independent EM runs; the model with the highest final likelihood is written to
     outputModel (utils.py:528).  sequences: space separated FASTA paths; alignments: exonerate cigar file."""
     from .realign import makeRealigner
+    if options.updateTheBand:
+        raise NotImplementedError("updateTheBand (re-deriving the guide alignments after every EM iteration) is not supported")
     batch, n = loadAlignments(sequences.split(), alignments, options.maxAlignmentLengthToSample, options.seed)
     if n == 0:
         raise RuntimeError("No alignments to train on in %s" % alignments)
@@ -230,7 +248,9 @@ def expectationMaximisationTrials(target, sequences, alignments, outputModel, op
     try:
         realigner.set_reference(batch.ref)
         for trial in range(options.trials):
-            if options.inputModel is not None:
+            if options.useDefaultModelAsStart:
+                hmm = _stock_start(options.modelType)
+            elif options.inputModel is not None:
                 hmm = Hmm.loadHmm(options.inputModel)
             elif options.randomStart:
                 hmm = _random_start(options.modelType, rng)

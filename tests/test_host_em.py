@@ -117,3 +117,26 @@ def test_do_em_through_the_mapper(tmp_path, oracle_engine, monkeypatch):
     from nanopore_b200.sam import Samfile
     recs = list(Samfile(sam_path, "r"))
     assert len(recs) == 4 and all(r.pos == 0 for r in recs)
+
+
+def test_symmetric_model_type_stays_symmetric_and_unsupported_options_raise(tmp_path):
+    """ADVICE r1: Options.modelType defaults to fiveState (the symmetric model): its M-step ties the X and Y gap states;
+    updateTheBand is refused instead of being ignored."""
+    rng = np.random.default_rng(3)
+    h = Hmm("fiveState")
+    assert h.type == 0
+    values = np.concatenate((rng.random(25) + 0.1, rng.random(80) + 0.1, [-123.0]))
+    em.mStep(h, values, trainEmissions=True)
+    t = np.array(h.transitions).reshape(5, 5)
+    e = np.array(h.emissions).reshape(5, 4, 4)
+    perm = [0, 2, 1, 4, 3]
+    assert np.allclose(t, t[np.ix_(perm, perm)]) and np.allclose(t.sum(axis=1), 1.0)
+    assert np.allclose(e, e[perm].transpose(0, 2, 1)) and np.allclose(e.reshape(5, -1).sum(axis=1), 1.0)
+    a = Hmm("fiveStateAsymmetric")
+    em.mStep(a, values, trainEmissions=True)
+    ta = np.array(a.transitions).reshape(5, 5)
+    assert not np.allclose(ta, ta[np.ix_(perm, perm)])                 # the asymmetric model is left alone
+    o = em.Options()
+    o.updateTheBand = True
+    with pytest.raises(NotImplementedError):
+        em.expectationMaximisationTrials(None, "", str(tmp_path / "none.cig"), str(tmp_path / "m.txt"), o)
