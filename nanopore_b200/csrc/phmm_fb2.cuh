@@ -158,6 +158,9 @@ __device__ __forceinline__ double logadd_k(double x, double y) {
 #elif PHMM_COEF_CONST == 2
 #define LA_M(x, y, ctab) logadd_k(x, y)
 #define LA_G(x, y, ctab) logadd_t(x, y, ctab)
+#elif PHMM_COEF_CONST == 3      // the gap-state chains (off the critical path of a cell) from constant memory
+#define LA_M(x, y, ctab) logadd_t(x, y, ctab)
+#define LA_G(x, y, ctab) logadd_k(x, y)
 #else
 #define LA_M(x, y, ctab) logadd_t(x, y, ctab)
 #define LA_G(x, y, ctab) logadd_t(x, y, ctab)
