@@ -295,8 +295,8 @@ int fb2_launch_t(const Fb2Args &a, int slots, size_t smem, cudaStream_t st) {
             return sw ? FN<2, true, false>(__VA_ARGS__) : FN<2, false, false>(__VA_ARGS__);          \
         }                                                                                            \
         if (nw == 4) {                                                                               \
-            if (ex) return sw ? FN<4, true, true>(__VA_ARGS__) : FN<4, false, true>(__VA_ARGS__);    \
-            return sw ? FN<4, true, false>(__VA_ARGS__) : FN<4, false, false>(__VA_ARGS__);          \
+            if (ex) return sw ? FN<PHMM_NW4, true, true>(__VA_ARGS__) : FN<PHMM_NW4, false, true>(__VA_ARGS__);    \
+            return sw ? FN<PHMM_NW4, true, false>(__VA_ARGS__) : FN<PHMM_NW4, false, false>(__VA_ARGS__);          \
         }                                                                                            \
         if (ex) return sw ? FN<8, true, true>(__VA_ARGS__) : FN<8, false, true>(__VA_ARGS__);        \
         return sw ? FN<8, true, false>(__VA_ARGS__) : FN<8, false, false>(__VA_ARGS__);              \

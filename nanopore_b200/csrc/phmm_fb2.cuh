@@ -62,7 +62,7 @@ constexpr int FB2_TAB = 16 + 25 * TS + 5 * TS + 5 * TS;   // logAdd coefficients
 // block takes the extra round of each diagonal wider than the block and its scheduler saturates while the others idle
 // at the barrier (profiles/r02a_k_fb2_ncu_metrics.txt: issue active 92 % max, 30 % min over the schedulers).
 #ifndef PHMM_NO_ROT
-#define FB2_ROT(diag) ((((diag) >> FB2_ROT_SHIFT) & (NW - 1)) << 5)
+#define FB2_ROT(diag) ((NW & (NW - 1)) ? 0 : ((((diag) >> FB2_ROT_SHIFT) & (NW - 1)) << 5))
 #else
 #define FB2_ROT(diag) 0
 #endif
@@ -427,10 +427,16 @@ __device__ __forceinline__ DiagRec ld_rec(const DiagRec *p) {
 }
 
 #ifndef PHMM_MB4
-#define PHMM_MB4 5
+#define PHMM_MB4 6              // launch bound of the 4-warp kernel: 80 registers (no spills); shared memory still holds 5 blocks per
+#endif                          // SM at 512 columns -- measured +1.5 % over the 96 registers of a bound of 5 (profiles/r02g_tune_warps.txt)
+#ifndef PHMM_NW4
+#define PHMM_NW4 4              // warps of the kernel the planner's "4 warps" class launches (tuning builds: 5, 6)
+#endif
+#ifndef PHMM_MB8
+#define PHMM_MB8 2
 #endif
 constexpr int fb2_min_blocks(int nw, bool expect) {
-    return expect ? (nw == 8 ? 2 : (nw == 4 ? 4 : 8)) : (nw == 8 ? 2 : (nw == 4 ? PHMM_MB4 : 8));
+    return expect ? (nw == 8 ? 2 : (nw == PHMM_NW4 ? (PHMM_NW4 == 4 ? 4 : PHMM_MB4) : 8)) : (nw == 8 ? PHMM_MB8 : (nw == PHMM_NW4 ? PHMM_MB4 : 8));
 }
 
 // Shared-memory diagonal buffers.  Cell (d, x) lives in column (x - (d >> 1)) & (wcap - 1) of the buffer of parity
