@@ -209,19 +209,17 @@ def _default_local_factory():
 
 
 def _concat_ranges(per_rank_data, per_rank_off, g_idx, n, dtype):
-    """Re-joins per-rank ragged results in input order: read g_idx[r][k] owns data_r[off_r[k]:off_r[k+1]]."""
-    lens = np.zeros(n, dtype=np.int64)
-    for idx, off in zip(g_idx, per_rank_off):
-        lens[idx] = off[1:] - off[:-1]
-    off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
-    out = np.zeros(int(off[-1]), dtype=dtype)
-    for idx, data, o in zip(g_idx, per_rank_data, per_rank_off):
-        if len(idx) == 0 or o[-1] == 0:
-            continue
-        ln = o[1:] - o[:-1]
-        dst = np.arange(int(o[-1]), dtype=np.int64) + np.repeat(off[idx] - o[:-1], ln)
-        out[dst] = data
-    return out, off
+    """Re-joins per-rank ragged results in input order: read g_idx[r][k] owns data_r[off_r[k]:off_r[k+1]].  The rows of all
+    ranks are laid end to end and gathered through the inverse of the sharding permutation (one native ragged gather)."""
+    from .batch import _gather_ranges
+    order = np.concatenate([np.asarray(i, dtype=np.int64) for i in g_idx]) if g_idx else np.zeros(0, np.int64)
+    assert len(order) == n
+    cat = np.concatenate([np.asarray(d, dtype=dtype) for d in per_rank_data]) if per_rank_data else np.zeros(0, dtype)
+    lens = np.concatenate([np.asarray(o[1:] - o[:-1], dtype=np.int64) for o in per_rank_off]) if per_rank_off else np.zeros(0, np.int64)
+    cat_off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    inv = np.empty(n, dtype=np.int64)
+    inv[order] = np.arange(n, dtype=np.int64)
+    return _gather_ranges(cat, cat_off, inv)
 
 
 class ShardedRealigner:
