@@ -96,18 +96,21 @@ def _native():
         return None
 
 
-def _gather_ranges(data, off, idx):
-    """data[off[i]:off[i+1]] for i in idx, concatenated, with the new offsets."""
+def _gather_ranges(data, off, idx, out=None):
+    """data[off[i]:off[i+1]] for i in idx, concatenated (into `out` when given), with the new offsets."""
     nat = _native()
     if nat is not None and len(idx) > 64:
-        return nat.gather_ranges(data, off, idx)
+        return nat.gather_ranges(data, off, idx, out=out)
     lens = off[idx + 1] - off[idx] if len(idx) else np.zeros(0, dtype=np.int64)
     new_off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
     total = int(new_off[-1])
     if total == 0:
-        return data[:0].copy(), new_off
+        return (data[:0].copy() if out is None else out), new_off
     pos = np.arange(total, dtype=np.int64) + np.repeat(off[idx] - new_off[:-1], lens)
-    return data[pos], new_off
+    if out is None:
+        return data[pos], new_off
+    np.take(data, pos, out=out)
+    return out, new_off
 
 
 def estimate_cells(batch, band=10, anchor_trim=14, split_side=3000):

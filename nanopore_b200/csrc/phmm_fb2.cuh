@@ -435,8 +435,14 @@ __device__ __forceinline__ DiagRec ld_rec(const DiagRec *p) {
 #ifndef PHMM_MB8
 #define PHMM_MB8 2
 #endif
+#ifndef PHMM_MBE
+#define PHMM_MBE 4              // launch bound of the 4-warp E-step kernel (126 registers at 4)
+#endif
+#ifndef PHMM_MBE2
+#define PHMM_MBE2 8             // ... of the 2-warp E-step kernel
+#endif
 constexpr int fb2_min_blocks(int nw, bool expect) {
-    return expect ? (nw == 8 ? 2 : (nw == PHMM_NW4 ? (PHMM_NW4 == 4 ? 4 : PHMM_MB4) : 8)) : (nw == 8 ? PHMM_MB8 : (nw == PHMM_NW4 ? PHMM_MB4 : 8));
+    return expect ? (nw == 8 ? 2 : (nw == PHMM_NW4 ? (PHMM_NW4 == 4 ? PHMM_MBE : PHMM_MB4) : PHMM_MBE2)) : (nw == 8 ? PHMM_MB8 : (nw == PHMM_NW4 ? PHMM_MB4 : 8));
 }
 
 // Shared-memory diagonal buffers.  Cell (d, x) lives in column (x - (d >> 1)) & (wcap - 1) of the buffer of parity

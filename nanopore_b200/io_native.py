@@ -80,14 +80,18 @@ def estimate_cells(in_ops, in_off, read_off, ref_start, ref_end, band, anchor_tr
     return out
 
 
-def gather_ranges(data, off, idx, threads=0):
-    """(rows idx of the ragged array (data, off) concatenated, new offsets) via phmm_io_gather_ranges."""
+def gather_ranges(data, off, idx, threads=0, out=None):
+    """(rows idx of the ragged array (data, off) concatenated, new offsets) via phmm_io_gather_ranges.  out: optional
+    destination (contiguous, same dtype, exactly the gathered size) -- e.g. a view into a staging buffer."""
     data = np.ascontiguousarray(data)
     off = np.ascontiguousarray(off, dtype=np.int64)
     idx = np.ascontiguousarray(idx, dtype=np.int64)
     lens = off[idx + 1] - off[idx] if len(idx) else np.zeros(0, dtype=np.int64)
     new_off = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
-    out = np.empty(int(new_off[-1]), dtype=data.dtype)
+    if out is None:
+        out = np.empty(int(new_off[-1]), dtype=data.dtype)
+    elif out.dtype != data.dtype or out.size != int(new_off[-1]) or not out.flags.c_contiguous:
+        raise ValueError("out must be a contiguous %s array of %d elements" % (data.dtype, int(new_off[-1])))
     rc = load_library().phmm_io_gather_ranges(_vp(data), _vp(off), _vp(idx), len(idx), data.dtype.itemsize, int(threads), _vp(out), _vp(new_off))
     if rc != 0:
         raise PhmmIoError("phmm_io_gather_ranges failed (%d)" % rc)

@@ -103,11 +103,65 @@ def _unpack(blob):
     return out
 
 
-def _send_blob(blob, dst):
+_staging = {}                      # destination rank -> reusable host staging buffer (pinned under NCCL)
+
+
+def _stage(dst, nbytes):
+    """Host staging buffer for the shard of rank dst: pinned memory when the transport is NCCL (the H2D copy is a DMA
+    straight out of it and does not block the host), grown on demand, reused from step to step."""
+    t = _staging.get(dst)
+    if t is None or t.numel() < nbytes:
+        cap = int(nbytes * 1.25) + 4096
+        t = torch.empty(cap, dtype=torch.uint8, pin_memory=(dist.get_backend() == "nccl"))
+        _staging[dst] = t
+    return t[:nbytes]
+
+
+def _pack_shard(batch, idx, dst):
+    """The wire blob of batch.subset(idx) gathered straight into rank dst's staging buffer: no intermediate sub-batch,
+    one pass over the shard's bases and guide ops (native ragged gather).  -> uint8 tensor (a view of the staging buffer)."""
+    from .batch import _gather_ranges
+    idx = np.asarray(idx, dtype=np.int64)
+    n = len(idx)
+    rl = batch.read_off[idx + 1] - batch.read_off[idx] if n else np.zeros(0, np.int64)
+    ol = batch.in_off[idx + 1] - batch.in_off[idx] if n else np.zeros(0, np.int64)
+    read_off = np.concatenate(([0], np.cumsum(rl))).astype(np.int64)
+    in_off = np.concatenate(([0], np.cumsum(ol))).astype(np.int64)
+    sizes = [(0, int(read_off[-1])), (1, n + 1), (1, n), (1, n), (2, int(in_off[-1])), (1, n + 1)]      # _BATCH_FIELDS order
+    head = np.array([len(sizes)] + [v for dt, sz in sizes for v in (dt, sz)], dtype=np.int64)
+    pos, o = [], 8 + 8 * head.size
+    for dt, sz in sizes:
+        nb = sz * _DT[dt].itemsize
+        pos.append((o, nb))
+        o += nb + (-nb) % 8
+    t = _stage(dst, o)
+    buf = t.numpy()
+    buf[:8] = np.array([head.size], dtype=np.int64).view(np.uint8)
+    buf[8:8 + 8 * head.size] = head.view(np.uint8)
+    view = lambda k, dt: buf[pos[k][0]:pos[k][0] + pos[k][1]].view(dt)
+    _gather_ranges(batch.reads, batch.read_off, idx, out=view(0, np.uint8))
+    view(1, np.int64)[:] = read_off
+    view(2, np.int64)[:] = batch.ref_start[idx]
+    view(3, np.int64)[:] = batch.ref_end[idx]
+    _gather_ranges(batch.in_ops, batch.in_off, idx, out=view(4, np.uint32))
+    view(5, np.int64)[:] = in_off
+    return t
+
+
+def _send_blob(blob, dst, wait=True):
+    """blob: numpy uint8 array or uint8 tensor (e.g. a pinned staging view).  wait=False returns the pending work and the
+    tensors it needs alive; the caller waits before the staging buffer is reused."""
     dev = _device()
-    dist.send(torch.tensor([blob.size], dtype=torch.int64, device=dev), dst)
-    if blob.size:
-        dist.send(torch.from_numpy(blob).to(dev), dst)
+    t = blob if isinstance(blob, torch.Tensor) else torch.from_numpy(blob)
+    n = torch.tensor([t.numel()], dtype=torch.int64, device=dev)
+    dist.send(n, dst)
+    if t.numel() == 0:
+        return None
+    td = t.to(dev, non_blocking=True)
+    if wait:
+        dist.send(td, dst)
+        return None
+    return dist.isend(td, dst), td, t
 
 
 def _recv_blob(src):
@@ -258,11 +312,18 @@ class ShardedRealigner:
             return self._sent[2]
         self._cmd(CMD_SET_BATCH)
         shards = shard_reads(read_cost(batch, params), dist.get_world_size())
+        pending = []
         for r in range(1, dist.get_world_size()):
-            sub = batch.subset(shards[r])
-            _send_blob(_pack([getattr(sub, f) for f in _BATCH_FIELDS]), r)
+            # packed straight into rank r's (pinned) staging buffer and sent without blocking: the transfer of shard r
+            # overlaps the packing of shard r + 1
+            pending.append(_send_blob(_pack_shard(batch, shards[r], r), r, wait=False))
         sub0 = batch.subset(shards[0])
         self._rl.set_batch([getattr(sub0, f) for f in _BATCH_FIELDS])
+        for w in pending:
+            if w is not None:
+                w[0].wait()
+        if pending and dist.get_backend() == "nccl":
+            torch.cuda.current_stream().synchronize()      # the staging buffers may be refilled from here on
         self._sent = (batch, key, shards)
         return shards
 
