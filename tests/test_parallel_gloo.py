@@ -122,3 +122,25 @@ def test_baseline_configs_script_dry_run_on_two_ranks(tmp_path):
     assert lines[0]["sample_equals_single_gpu"] and lines[0]["cigars_span_reads"] and len(lines[0]["rank_cells"]) == 2
     assert lines[1]["sample_statistics_equal_single_gpu"] and lines[1]["monotone"] and len(lines[1]["running_likelihoods"]) == 5
     assert lines[2]["sample_equals_single_gpu"] and lines[2]["reads"] == 20 and min(lines[2]["rank_cells"]) > 0
+
+
+def test_pack_shard_equals_pack_of_subset():
+    """The scatter packs a shard straight into its staging buffer (native ragged gather): same wire blob content as
+    packing batch.subset(idx), for ordinary, single-read and empty shards."""
+    import torch.distributed as dist
+    created = False
+    if not dist.is_initialized():
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(free_port()), RANK="0", WORLD_SIZE="1")
+        dist.init_process_group("gloo")
+        created = True
+    try:
+        b = synth.make_batch(300, 400, 3000, seed=2)
+        rng = np.random.default_rng(1)
+        for idx in (np.sort(rng.choice(300, 120, replace=False)), np.array([7]), np.zeros(0, np.int64), np.arange(300)):
+            got = parallel._unpack(parallel._pack_shard(b, idx, 1).numpy().copy())
+            sub = b.subset(idx)
+            for a, f in zip(got, parallel._BATCH_FIELDS):
+                assert np.array_equal(a, getattr(sub, f)) and a.dtype == getattr(sub, f).dtype, f
+    finally:
+        if created:
+            dist.destroy_process_group()
