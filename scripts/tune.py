@@ -26,6 +26,8 @@ for spec in sys.argv[2:] or [""]:
     for kv in [s for s in spec.split(",") if s]:
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
+    if os.environ.get("MEM_BUDGET_GB"):                  # fewer resident regions per SM: how throughput scales with occupancy
+        ctx.set_memory_budget(int(float(os.environ["MEM_BUDGET_GB"]) * 1e9))
     ctx.set_reference(b.ref)
     ctx.prepare(b.reads, b.read_off, b.ref_start, b.ref_end, b.in_ops, b.in_off, capi.default_params(band=band))
     ctx.run()
