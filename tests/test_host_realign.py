@@ -199,3 +199,30 @@ def test_command_line_entry_point(tmp_path, oracle_engine):
     chained = str(tmp_path / "chained.sam")
     realign.chainSamFile(sam_path, chained, fq, ref_fa)
     check_against_oracle(ref_fa, fq, out, chained, oracle.Model(), 0.4, 0.0)
+
+
+def test_realign_variant_classes_of_a_base_mapper(tmp_path, oracle_engine, monkeypatch):
+    """The six `*Chain` / `*Realign*` variants the reference writes out for every base mapper (last_params.py:10-38),
+    derived from a stand-in base mapper: each one runs the base, then chains / realigns with its variant's arguments."""
+    from nanopore_b200 import em
+    from nanopore_b200.mappers import realignVariants as rv
+    from nanopore_b200.sam import Samfile
+    fast = em.Options()                                       # the reference's 3 x 100 schedule is for GPUs, not for the CPU checker
+    fast.modelType, fast.randomStart, fast.trials, fast.iterations, fast.trainEmissions = "fiveStateAsymmetric", True, 1, 2, True
+    orig = em.learnModelFromSamFileTargetFn
+    monkeypatch.setattr(em, "learnModelFromSamFileTargetFn", lambda t, *a: orig(t, *a, options=fast))
+    assert sorted(rv.realignVariants(rv.SamFileMapper)) == sorted("SamFileMapper" + s for s in rv.VARIANTS)
+    ref_fa, fq, sam_path, _ = make_experiment(str(tmp_path / "exp"), n_reads=5, read_len=300, seed=41)
+    outs = {}
+    for name in ("SamFileMapperChain", "SamFileMapperRealign", "SamFileMapperRealignTrainedModel40", "SamFileMapperRealignEm"):
+        out = str(tmp_path / (name + ".sam"))
+        m = getattr(rv, name)(fq, "2D", ref_fa, out, emptyHmmFile=str(tmp_path / (name + "_hmm.txt")), mappedSamFile=sam_path)
+        assert Stack(m).startJobTree(None) == 0
+        outs[name] = [(aR.qname, aR.pos, tuple(aR.cigar)) for aR in Samfile(out, "r") if aR.rname != -1]
+    chain = outs["SamFileMapperChain"]
+    assert len(chain) == 5 and all(pos == 0 for _, pos, _ in chain)                   # one global alignment per read
+    for name in ("SamFileMapperRealign", "SamFileMapperRealignTrainedModel40", "SamFileMapperRealignEm"):
+        assert [q for q, _, _ in outs[name]] == [q for q, _, _ in chain]                   # same records, same order
+        assert any(c != c0 for (_, _, c), (_, _, c0) in zip(outs[name], chain))            # new cigars
+    assert outs["SamFileMapperRealignTrainedModel40"] != outs["SamFileMapperRealign"]      # the trained model was used
+    assert os.path.exists(str(tmp_path / "SamFileMapperRealignEm_hmm.txt"))                # doEm trained into emptyHmmFile
