@@ -167,3 +167,32 @@ def test_margin_align_snp_caller_on_gpu_equals_checker(tmp_path):
                 realign.setRealignerFactory(prev)
         outs.append(os.path.join(outdir, "marginaliseConsensus.xml"))
     assert filecmp.cmp(outs[0], outs[1], shallow=False)
+
+
+def test_base_expectation_api_error_paths():
+    """Call-order and argument errors of phmm_base_expectations_* come back as error codes with text, not as crashes."""
+    b = synth.make_batch(3, 200, 800, seed=5)
+    p = posteriors.posteriorParams()
+    ctx = capi.PhmmContext(0)
+    with pytest.raises(capi.PhmmError):
+        ctx.base_expectations_reset()                                   # no reference yet
+    ctx.set_reference(b.ref)
+    with pytest.raises(capi.PhmmError):
+        ctx.base_expectations_fetch(len(b.ref))                         # nothing accumulated
+    ctx.base_expectations_reset(2)
+    with pytest.raises(capi.PhmmError):
+        ctx.add_base_expectations()                                     # no batch prepared
+    ctx.prepare(b.reads, b.read_off, b.ref_start, b.ref_end, b.in_ops, b.in_off, p)
+    with pytest.raises(capi.PhmmError):
+        ctx.add_base_expectations(table=2)                              # only tables 0 and 1 exist
+    with pytest.raises(ValueError):
+        ctx.add_base_expectations(read_mask=np.ones(2, np.uint8))       # one byte per read
+    ctx.add_base_expectations(table=1)                                  # runs the batch itself when it has not run yet
+    t0, t1 = ctx.base_expectations_fetch(len(b.ref), 0), ctx.base_expectations_fetch(len(b.ref), 1)
+    assert t0.sum() == 0 and t1.sum() > 0
+    with pytest.raises(capi.PhmmError):
+        ctx.base_expectations_fetch(len(b.ref) - 1, 1)                  # wrong size
+    ctx.set_reference(b.ref)                                            # a new reference drops the tables
+    with pytest.raises(capi.PhmmError):
+        ctx.base_expectations_fetch(len(b.ref), 1)
+    ctx.close()
