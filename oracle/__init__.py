@@ -104,7 +104,7 @@ UP_UNFUSED_HORNER, UP_LIBM_EXP, UP_GREEDY_ORDER = 1, 2, 4
 
 
 def set_upstream_arithmetic(flags):
-    """Differential runs only (scripts/differential.py): bit mask of UP_* that replaces the documented deviations of the
+    """Differential runs only (tests/tools/differential.py): bit mask of UP_* that replaces the documented deviations of the
     oracle (header of phmm_oracle.c, items 1-3) by the recalled upstream behaviour.  0 = the arithmetic the CUDA library
     implements."""
     lib().po_set_upstream_arithmetic(int(flags))

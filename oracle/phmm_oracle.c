@@ -40,7 +40,7 @@
  *
  * Each of (1)-(3) has a switch (po_set_upstream_arithmetic, bits PO_UP_*) that
  * replaces it by the recalled upstream behaviour, so that a differential run
- * against a real cactus_realign binary (scripts/differential.py) can tell which
+ * against a real cactus_realign binary (tests/tools/differential.py) can tell which
  * deviation a mismatch comes from.  The CUDA library implements the default
  * (switches off) arithmetic only.
  *

@@ -1,4 +1,4 @@
-"""scripts/differential.py: the plumbing of the differential run -- FASTA files, the exonerate cigar
+"""tests/tools/differential.py: the plumbing of the differential run -- FASTA files, the exonerate cigar
 on stdin, flags, the printed cigar -- exercised against a stand-in `cactus_realign` executable that answers with the CPU
 checker (the real binary does not exist in this environment; with it the same script pins or refutes upstream parity)."""
 import importlib.util
@@ -32,7 +32,7 @@ def test_differential_script_against_a_stand_in_binary(tmp_path, capsys):
     shim = tmp_path / "cactus_realign"
     shim.write_text(SHIM % (sys.executable, ROOT))
     shim.chmod(shim.stat().st_mode | stat.S_IEXEC)
-    spec = importlib.util.spec_from_file_location("differential", os.path.join(ROOT, "scripts", "differential.py"))
+    spec = importlib.util.spec_from_file_location("differential", os.path.join(ROOT, "tests", "tools", "differential.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.main(["--binary", str(tmp_path / "missing")]) == 2

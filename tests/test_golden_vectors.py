@@ -1,4 +1,4 @@
-"""Committed golden vectors (tests/golden/oracle_vectors.json, made by scripts/make_golden.py) pin the oracle's
+"""Committed golden vectors (tests/golden/oracle_vectors.json, made by tests/tools/make_golden.py) pin the oracle's
 arithmetic: logAdd / exp bit patterns, CIGARs, posterior pair sets, MEA scores and E-step integers.  The GPU test
 checks the library against the same file, so kernel and oracle are pinned to one committed answer."""
 import json
@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "scripts"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
 import make_golden                                  # noqa: E402
 
 import oracle                                       # noqa: E402

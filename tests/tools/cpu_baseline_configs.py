@@ -1,16 +1,16 @@
 """CPU baseline of BASELINE.json configs[2..4]: the CPU port (oracle/, the stand-in for the
 reference's cactus_realign, which cannot be built here) timed on a bounded sample of each config's reads, one read
 per task like the reference's job farm (reference nanopore/analyses/utils.py:565-570), on all host cores and on the 4
-workers of the reference's default (Makefile:1).  Prints one JSON line per config.  Test / measurement infrastructure:
-the only scripts that import oracle/ are the CPU legs of the benchmarks.
-usage: python scripts/cpu_baseline_configs.py [reads_per_core=2]"""
+workers of the reference's default (Makefile:1).  Prints one JSON line per config.  Test / measurement infrastructure
+(lives under tests/: nothing outside tests/, smoke() and bench.py's CPU legs touches oracle/).
+usage: python tests/tools/cpu_baseline_configs.py [reads_per_core=2]"""
 import json
 import os
 import sys
 import time
 from concurrent.futures import ThreadPoolExecutor
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle                                               # noqa: E402
 from nanopore_b200 import synth                             # noqa: E402
 

@@ -1,6 +1,6 @@
 """Differential run of a real `cactus_realign` binary against the CPU oracle.
 
-    python scripts/differential.py --binary /path/to/cactus_realign [--reads 20] [--read-len 2000] [--band 10]
+    python tests/tools/differential.py --binary /path/to/cactus_realign [--reads 20] [--read-len 2000] [--band 10]
 
 For every synthetic read the script does what the reference does (reference nanopore/analyses/utils.py:576-589): writes
 ref.fa / read.fa, pipes the exonerate cigar line into
@@ -17,7 +17,7 @@ import subprocess
 import sys
 import tempfile
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np                                                     # noqa: E402
 
 import oracle                                                          # noqa: E402

@@ -1,7 +1,7 @@
 """E-step throughput (BASELINE.json configs[3] shape at reduced read count): Baum-Welch iterations over N reads x 8 kb
 vs a 50 kb reference, realign options of the reference's EM (--diagonalExpansion=10 --splitMatrixBiggerThanThis=300,
 reference nanopore/analyses/utils.py:511).  Prints one JSON line; the CPU oracle is timed on a sample beside it.
-usage: python scripts/em_bench.py [reads] [iterations]"""
+usage: python tests/tools/em_bench.py [reads] [iterations]"""
 import json
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle                                               # noqa: E402  (CPU baseline leg only)
 from nanopore_b200 import capi, em, synth                   # noqa: E402
 from nanopore_b200.engine import Realigner                  # noqa: E402

@@ -1,6 +1,6 @@
 """First-light check on a GPU box: GPU library vs CPU oracle on small seeded batches."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import oracle
 from nanopore_b200 import synth, capi
@@ -52,7 +52,7 @@ def main():
         ctx.set_reference(b.ref)
         bad += compare(ctx, model, b, capi.default_params(band=band), oracle.make_params(expansion=band), "stock band=%d" % band)
     # trained asymmetric model
-    h = Hmm.loadHmm(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "blasr_hmm_0.txt"))
+    h = Hmm.loadHmm(os.path.join(os.path.dirname(__file__), "..", "golden", "blasr_hmm_0.txt"))
     t, e = h.arrays()
     ctx2 = capi.PhmmContext(0, t, e, 1)
     model2 = oracle.Model(t, e)

@@ -1,7 +1,7 @@
 """Generates tests/golden/oracle_vectors.json: seeded inputs -> CIGARs, posterior checksums, MEA scores and E-step
 integers of the CPU oracle.  Committed so that later refactors of the oracle (and, through the GPU parity tests, of
 the kernels) are pinned to today's arithmetic.  Parity with upstream cactus_realign stays unpinned.
-usage: python scripts/make_golden.py"""
+usage: python tests/tools/make_golden.py"""
 import hashlib
 import json
 import os
@@ -9,7 +9,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import oracle                                   # noqa: E402
 from nanopore_b200 import synth                 # noqa: E402
@@ -50,7 +50,7 @@ def run_case(c):
 
 
 if __name__ == "__main__":
-    out = {"generator": "scripts/make_golden.py", "note": "oracle outputs (parity with upstream unpinned)",
+    out = {"generator": "tests/tools/make_golden.py", "note": "oracle outputs (parity with upstream unpinned)",
            "logadd": [[x, y, oracle.logadd(x, y).hex()] for x, y in [(0.0, 0.0), (-1.5, -0.25), (-3.0, 2.0), (1.0, -6.4), (-10.0, 0.0), (-700.0, -701.0)]],
            "exp": [[x, oracle.exp(x).hex()] for x in (0.0, -0.01, -4.60517, -20.0, -699.0)],
            "cases": [run_case(c) for c in CASES]}
