@@ -205,8 +205,11 @@ int phmm_set_memory_budget(phmm_ctx *ctx, int64_t bytes);
 /* Tuning / test switches of the library itself (no counterpart in the reference).  Names:
  *   "legacy_kernel" 1: run the first-generation kernel (forward window wholly in HBM) instead of the
  *                      windowed shared-memory kernel; results are identical
- *   "decode_full_sweep" 1: the decode kernel sweeps every diagonal of the band instead of skipping stretches of
- *                      diagonals that hold no posterior pair; results are identical
+ *   "decode_block"  1: every region is decoded by the block-per-region kernel on the band of the forward sweep
+ *                      (k_decode) instead of the warp-per-region kernel on the envelope of its posterior pairs
+ *                      (k_decode_w); results are identical
+ *   "decode_full_sweep" 1: as decode_block, and the kernel sweeps every diagonal of the band instead of skipping
+ *                      stretches of diagonals that hold no posterior pair; results are identical
  *   "warps"         0 = choose by band width, else 2, 4 or 8 warps per DP region
  *   "smem_columns"  0 = choose, else the shared-memory diagonal buffer (power of two, 64..1024)
  *   "candidate_cap" / "candidate_eps_ppm"  capacity and tolerance (1e-6 log units, default 20000) of the posterior

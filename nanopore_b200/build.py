@@ -6,7 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libphmm_sm100.so")
 SOURCES = ["phmm_api.cu"]
-HEADERS = ["phmm_device.cuh", "phmm_kernels.cuh", "phmm_fb2.cuh", os.path.join("..", "..", "include", "phmm.h")]
+HEADERS = ["phmm_device.cuh", "phmm_kernels.cuh", "phmm_fb2.cuh", "phmm_decode_w.cuh", os.path.join("..", "..", "include", "phmm.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

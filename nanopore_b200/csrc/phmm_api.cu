@@ -17,6 +17,7 @@
 
 #include "../../include/phmm.h"
 #include "phmm_fb2.cuh"
+#include "phmm_decode_w.cuh"
 
 using namespace phmm;
 
@@ -60,6 +61,7 @@ struct BatchState {
     std::vector<int64_t> read_lx, read_ly;
     int nw = 1;
     int fb_slots = 0, dec_slots = 0;
+    int32_t nd_stride = 0;                       // ints per decode slot in the per-diagonal arrays
     int64_t ring_cells = 0; int32_t dcap = 0, bw = 0;
     int32_t max_lx = 0, max_ly = 0, max_nd = 0, max_pairs = 0;
     int64_t total_pair_cap = 0, total_mrun_cap = 0;
@@ -86,7 +88,7 @@ struct phmm_ctx {
     std::string err;
     DevModel model;
     int64_t mem_budget = 0;
-    bool force_legacy = false, decode_full_sweep = false;
+    bool force_legacy = false, decode_full_sweep = false, decode_block = false;
     int opt_warps = 0, opt_wcap = 0, opt_dbg = 0, opt_ccap = 0;
     double opt_est_eps = 0.02;             // tests: run the first-generation kernel (k_fwdbwd) instead of k_fb2
     DevBuf d_ref; int64_t ref_len = -1;
@@ -96,6 +98,7 @@ struct phmm_ctx {
     DevBuf d_px, d_py, d_pw, d_npairs;
     DevBuf d_expT, d_expE, d_expLL;
     DevBuf d_sumx, d_sumy, d_dstart, d_dfill, d_sidx, d_wre, d_pred, d_colmap, d_sring, d_lring;
+    DevBuf d_by, d_blo, d_bhi, d_fblist;         // k_decode_w: sorted y, envelope per diagonal, regions left to k_decode
     DevBuf d_mrx, d_mry, d_mrn, d_nmruns, d_score;
     DevBuf d_cx, d_cy, d_cn, d_coff;
     DevBuf d_baseexp, d_readmask; int64_t baseexp_len = -1; int32_t baseexp_tables = 0;   // tables of 5 x reference length sums of posterior mass per read base (A C G T other)
@@ -319,7 +322,7 @@ void release_scratch(phmm_ctx *ctx) {
     DevBuf *all[] = {&ctx->d_fring, &ctx->d_dtab, &ctx->d_bring, &ctx->d_dots, &ctx->d_ring, &ctx->d_wide, &ctx->d_fsave, &ctx->d_totals,
                      &ctx->d_recs, &ctx->d_recoff, &ctx->d_cand, &ctx->d_px, &ctx->d_py, &ctx->d_pw, &ctx->d_npairs, &ctx->d_expT, &ctx->d_expE,
                      &ctx->d_expLL, &ctx->d_sumx, &ctx->d_sumy, &ctx->d_dstart, &ctx->d_dfill, &ctx->d_sidx, &ctx->d_wre, &ctx->d_pred,
-                     &ctx->d_colmap, &ctx->d_sring, &ctx->d_lring, &ctx->d_mrx, &ctx->d_mry, &ctx->d_mrn, &ctx->d_nmruns, &ctx->d_score,
+                     &ctx->d_colmap, &ctx->d_sring, &ctx->d_lring, &ctx->d_by, &ctx->d_blo, &ctx->d_bhi, &ctx->d_fblist, &ctx->d_mrx, &ctx->d_mry, &ctx->d_mrn, &ctx->d_nmruns, &ctx->d_score,
                      &ctx->d_cx, &ctx->d_cy, &ctx->d_cn, &ctx->d_coff};
     for (DevBuf *d : all) d->release();
 }
@@ -390,12 +393,15 @@ int plan_memory(phmm_ctx *ctx) {
     // fixed allocations
     const int64_t fixed = b.total_pair_cap * 12 + b.total_mrun_cap * 12 + nreg * (sizeof(Region) + sizeof(RegionGeom) + 64) +
                           (b.fast ? b.rec_off[nreg] * (int64_t)sizeof(DiagRec) + nreg * 8 : 0);
-    const int64_t dec_slot_bytes = (int64_t)(b.max_lx + 1) * 4 + (int64_t)(b.max_ly + 1) * 4 + (int64_t)(b.max_nd + 4) * 8 +
-                                   (int64_t)(b.max_pairs + 1) * 16 + (int64_t)2 * (b.max_lx + 2) * 8 + (int64_t)4 * b.bw * 12;
+    // decode slots serve both kernels: k_decode_w (one warp per region, DW_BLOCKS per SM) and k_decode for the regions it
+    // leaves; they share sumx, sumy, dstart, dfill / nxt, sidx / bx, wre / bwr and pred
+    b.nd_stride = (b.max_nd + 4 + 3) & ~3;
+    const int64_t dec_slot_bytes = (int64_t)(b.max_lx + 1) * 4 + (int64_t)(b.max_ly + 1) * 4 + (int64_t)b.nd_stride * 16 +
+                                   (int64_t)(b.max_pairs + 1) * 20 + (int64_t)2 * (b.max_lx + 2) * 8 + (int64_t)4 * b.bw * 12;
     int64_t avail = budget(ctx) - fixed;
     if (avail < slot_bytes + dec_slot_bytes) return fail(ctx, PHMM_E_NOMEM, "memory budget too small for one region of this batch");
     // measured (profiles/r01b_phase_breakdown.txt, tune15): 2-warp decode blocks, 16 per SM, beat 4 warps x 8
-    int64_t dec_want = (int64_t)ctx->sm_count * (b.nw >= 2 ? 16 : 8);
+    int64_t dec_want = (int64_t)ctx->sm_count * std::max(DW_BLOCKS, b.nw >= 2 ? 16 : 8);
     dec_want = std::min<int64_t>(dec_want, nreg);
     dec_want = std::max<int64_t>(1, std::min<int64_t>(dec_want, (avail / 4) / dec_slot_bytes));
     avail -= dec_want * dec_slot_bytes;
@@ -437,8 +443,12 @@ int plan_memory(phmm_ctx *ctx) {
         } else {
             TRY(ctx->d_sumx.ensure((size_t)dec_want * (b.max_lx + 1) * 4));
             TRY(ctx->d_sumy.ensure((size_t)dec_want * (b.max_ly + 1) * 4));
-            TRY(ctx->d_dstart.ensure((size_t)dec_want * (b.max_nd + 4) * 4));
-            TRY(ctx->d_dfill.ensure((size_t)dec_want * (b.max_nd + 4) * 4));
+            TRY(ctx->d_dstart.ensure((size_t)dec_want * b.nd_stride * 4));
+            TRY(ctx->d_dfill.ensure((size_t)dec_want * b.nd_stride * 4));
+            TRY(ctx->d_blo.ensure((size_t)dec_want * b.nd_stride * 4));
+            TRY(ctx->d_bhi.ensure((size_t)dec_want * b.nd_stride * 4));
+            TRY(ctx->d_by.ensure((size_t)dec_want * (b.max_pairs + 1) * 4));
+            TRY(ctx->d_fblist.ensure((size_t)nreg * 4 + 16));
             TRY(ctx->d_sidx.ensure((size_t)dec_want * (b.max_pairs + 1) * 4));
             TRY(ctx->d_wre.ensure((size_t)dec_want * (b.max_pairs + 1) * 8));
             TRY(ctx->d_pred.ensure((size_t)dec_want * (b.max_pairs + 1) * 4));
@@ -627,8 +637,30 @@ int do_run(phmm_ctx *ctx) {
         da.regular = reinterpret_cast<const int32_t *>(ctx->d_geom.as<char>() + offsetof(RegionGeom, regular));
         da.regular_stride = ctx->decode_full_sweep ? 0 : (int32_t)(sizeof(RegionGeom) / 4);
         if (ctx->decode_full_sweep) da.regular = ctx->d_counter.as<int32_t>() + 4;      // a zero: no region takes the shortcut
-        if (b.nw == 1) k_decode<1><<<b.dec_slots, 32, 0, ctx->stream>>>(da);
-        else k_decode<2><<<b.dec_slots, 64, 0, ctx->stream>>>(da);
+        const bool block_only = ctx->decode_full_sweep || ctx->decode_block;
+        if (!block_only) {
+            // the envelope kernel first; what it cannot take (irregular band, very wide envelope) is left in d_fblist
+            DecWArgs dw;
+            memset(&dw, 0, sizeof(dw));
+            dw.regions = da.regions; dw.order = da.order; dw.n_regions = da.n_regions;
+            dw.counter = ctx->d_counter.as<int32_t>() + 9;
+            dw.p = b.dp;
+            dw.px = da.px; dw.py = da.py; dw.pw = da.pw; dw.npairs = da.npairs;
+            dw.regular = da.regular; dw.regular_stride = da.regular_stride;
+            dw.sumx = da.sumx; dw.sumy = da.sumy; dw.max_lx = b.max_lx; dw.max_ly = b.max_ly;
+            dw.dstart = da.dstart; dw.nxt = da.dfill; dw.blo = ctx->d_blo.as<int32_t>(); dw.bhi = ctx->d_bhi.as<int32_t>();
+            dw.nd_stride = b.nd_stride;
+            dw.bx = da.sidx; dw.by = ctx->d_by.as<int32_t>(); dw.bwr = da.wre; dw.pred = da.pred; dw.max_pairs = b.max_pairs;
+            dw.fb_list = ctx->d_fblist.as<int32_t>(); dw.fb_count = ctx->d_counter.as<int32_t>() + 10;
+            dw.mrx = da.mrx; dw.mry = da.mry; dw.mrn = da.mrn; dw.nmruns = da.nmruns; dw.score = da.score;
+            k_decode_w<<<b.dec_slots, 32, 0, ctx->stream>>>(dw);
+            CK(cudaGetLastError());
+            b.stats.launches++; b.stats.run_launches++;
+            da.order = dw.fb_list; da.n_dev = dw.fb_count;
+        }
+        const int old_slots = std::min<int>(b.dec_slots, ctx->sm_count * (b.nw >= 2 ? 16 : 8));
+        if (b.nw == 1) k_decode<1><<<old_slots, 32, 0, ctx->stream>>>(da);
+        else k_decode<2><<<old_slots, 64, 0, ctx->stream>>>(da);
         CK(cudaGetLastError());
         b.stats.launches++; b.stats.run_launches++;
     }
@@ -759,6 +791,7 @@ int phmm_set_option(phmm_ctx *ctx, const char *name, int64_t value) {
     const std::string n(name);
     if (n == "legacy_kernel") ctx->force_legacy = value != 0;
     else if (n == "decode_full_sweep") ctx->decode_full_sweep = value != 0;
+    else if (n == "decode_block") ctx->decode_block = value != 0;
     else if (n == "warps") {
         if (value != 0 && value != 2 && value != 4 && value != 8) return fail(ctx, PHMM_E_ARG, "warps must be 0, 2, 4 or 8");
         ctx->opt_warps = (int)value;

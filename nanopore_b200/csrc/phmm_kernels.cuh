@@ -554,6 +554,8 @@ struct DecArgs {
     const Run *runs;
     const int32_t *order;
     int32_t n_regions;
+    const int32_t *n_dev;                                     // not NULL: the number of regions in `order` lives on the device
+                                                              // (the list k_decode_w leaves behind, phmm_decode_w.cuh)
     int32_t *counter;
     DevParams p;
     const int32_t *px, *py, *pw;
@@ -589,13 +591,14 @@ __global__ void __launch_bounds__(NW * 32) k_decode(const __grid_constant__ DecA
     int64_t *const colmap = a.colmap + (int64_t)slot * 2 * (a.max_lx + 2);
     int64_t *const sr = a.sring + (int64_t)slot * 4 * a.bw;
     int32_t *const lr = a.lring + (int64_t)slot * 4 * a.bw;
+    const int n_regions = a.n_dev ? *a.n_dev : a.n_regions;
 
     for (;;) {
         block_sync<NW>();
         if (tid == 0) s_region = atomicAdd(a.counter, 1);
         block_sync<NW>();
         const int qi = s_region;
-        if (qi >= a.n_regions) break;
+        if (qi >= n_regions) break;
         const int ridx = a.order[qi];
         const Region reg = a.regions[ridx];
         const int lx = reg.lx, ly = reg.ly, nd = lx + ly;

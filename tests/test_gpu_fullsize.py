@@ -62,6 +62,7 @@ def config2():
     {"candidate_cap": 64},                         # the candidate list overflows in every window
     {"warps": 2},
     {"warps": 8},
+    {"decode_block": 1},                           # block-per-region decode on the band instead of the envelope kernel
 ])
 def test_config2_shape_posteriors_and_cigars(config2, opts):
     b, want = config2

@@ -245,6 +245,7 @@ def test_prepare_run_fetch_split_form():
 @pytest.mark.parametrize("opts", [
     {"legacy_kernel": 1},
     {"decode_full_sweep": 1},
+    {"decode_block": 1},                        # k_decode on the band for every region instead of k_decode_w on the envelope
     {"warps": 2}, {"warps": 4}, {"warps": 8},
     {"smem_columns": 64},                       # most diagonals take the wide (global buffer) path
     {"smem_columns": 64, "warps": 2},

@@ -1,0 +1,102 @@
+// decode_w_emu.cpp -- runs the UNCHANGED source of k_decode_w (nanopore_b200/csrc/phmm_decode_w.cuh) on the host: the
+// 32 lanes of its one-warp block are 32 fibers that switch at every warp synchronisation point (see cuda_runtime.h in
+// this directory).  tests/test_decode_w_emulated.py feeds it the checker's posterior pairs and compares the chain it
+// returns with the checker's.  Test infrastructure only.
+#include <stdio.h>
+#include <stdlib.h>
+#include <ucontext.h>
+#include <vector>
+
+#include "cuda_runtime.h"
+#include "../../../nanopore_b200/csrc/phmm_decode_w.cuh"
+
+namespace warp_emu {
+unsigned long long slot[32];
+static ucontext_t main_ctx, ctx[32];
+static int cur = 0, done[32];
+static long arrived[32];
+static unsigned order_seed = 1;
+static const phmm::DecWArgs *g_args;
+
+int lane() { return cur; }
+static void yield() { swapcontext(&ctx[cur], &main_ctx); }
+void barrier() {
+    const long g = ++arrived[cur];
+    for (;;) {
+        bool all = true;
+        for (int l = 0; l < 32; l++) if (!done[l] && arrived[l] < g) { all = false; break; }
+        if (all) return;
+        yield();
+    }
+}
+static void entry() {
+    phmm::k_decode_w(*g_args);
+    done[cur] = 1;
+    yield();
+}
+// runs one warp to completion; the order in which runnable lanes are resumed is shuffled per round (seed != 0) so that
+// a missing synchronisation shows as a wrong result for some seed
+static void run_warp(const phmm::DecWArgs &a, unsigned seed) {
+    g_args = &a;
+    order_seed = seed;
+    std::vector<std::vector<char>> stacks(32, std::vector<char>(1 << 18));
+    for (int l = 0; l < 32; l++) {
+        done[l] = 0; arrived[l] = 0;
+        getcontext(&ctx[l]);
+        ctx[l].uc_stack.ss_sp = stacks[l].data();
+        ctx[l].uc_stack.ss_size = stacks[l].size();
+        ctx[l].uc_link = &main_ctx;
+        makecontext(&ctx[l], entry, 0);
+    }
+    int perm[32];
+    for (int l = 0; l < 32; l++) perm[l] = l;
+    for (;;) {
+        bool any = false;
+        if (seed) for (int l = 31; l > 0; l--) { order_seed = order_seed * 1664525u + 1013904223u; const int j = (order_seed >> 8) % (l + 1); std::swap(perm[l], perm[j]); }
+        for (int q = 0; q < 32; q++) {
+            const int l = perm[q];
+            if (done[l]) continue;
+            any = true;
+            cur = l;
+            swapcontext(&main_ctx, &ctx[l]);
+        }
+        if (!any) break;
+    }
+}
+}  // namespace warp_emu
+
+// One region: pairs (px, py, pw) in region-local sequence coordinates.  Returns the number of match runs written
+// (reverse order) or -1 when the kernel left the region to k_decode; *score receives the chain score.
+extern "C" int emu_decode_w(int lx, int ly, int np, const int32_t *px, const int32_t *py, const int32_t *pw, double gap_gamma,
+                            double match_gamma, int regular, unsigned seed, int32_t *mrx, int32_t *mry, int32_t *mrn, int mrun_cap,
+                            int64_t *score, int32_t *envelope_cells) {
+    using namespace phmm;
+    Region reg;
+    memset(&reg, 0, sizeof(reg));
+    reg.lx = lx; reg.ly = ly; reg.pair_off = 0; reg.pair_cap = np; reg.mrun_off = 0; reg.mrun_cap = mrun_cap;
+    const int nd = lx + ly, stride = (nd + 4 + 3) & ~3;
+    std::vector<int32_t> sumx(lx + 1), sumy(ly + 1), dstart(stride), nxt(stride), blo(stride), bhi(stride), bx(np + 1), by(np + 1), pred(np + 1);
+    std::vector<int64_t> bwr(np + 1);
+    // stale scratch of an earlier region must not matter
+    for (auto *v : {&sumx, &sumy, &dstart, &nxt, &blo, &bhi, &bx, &by, &pred}) for (auto &e : *v) e = 0x5a5a5a5a;
+    int32_t order = 0, counter = 0, npairs = np, fb_list[1] = {-1}, fb_count = 0, nmruns = -7;
+    DecWArgs a;
+    memset(&a, 0, sizeof(a));
+    a.regions = &reg; a.order = &order; a.n_regions = 1; a.counter = &counter;
+    a.p.gap_gamma = gap_gamma; a.p.match_gamma = match_gamma;
+    a.px = px; a.py = py; a.pw = pw; a.npairs = &npairs;
+    a.regular = &regular; a.regular_stride = 0;
+    a.sumx = sumx.data(); a.sumy = sumy.data(); a.max_lx = lx; a.max_ly = ly;
+    a.dstart = dstart.data(); a.nxt = nxt.data(); a.blo = blo.data(); a.bhi = bhi.data(); a.nd_stride = stride;
+    a.bx = bx.data(); a.by = by.data(); a.bwr = bwr.data(); a.pred = pred.data(); a.max_pairs = np;
+    a.fb_list = fb_list; a.fb_count = &fb_count;
+    a.mrx = mrx; a.mry = mry; a.mrn = mrn; a.nmruns = &nmruns; a.score = score;
+    warp_emu::run_warp(a, seed);
+    if (envelope_cells) {
+        long c = 0;
+        for (int d = 0; d <= nd; d++) c += bhi[d] - blo[d] + 1;
+        *envelope_cells = (int32_t)std::min<long>(c, 0x7fffffff);
+    }
+    if (fb_count) return -1;
+    return nmruns;
+}
