@@ -125,6 +125,12 @@ __global__ void __launch_bounds__(32, DW_BLOCKS) k_decode_w(const __grid_constan
             continue;
         }
         const int np = min(a.npairs[ridx], reg.pair_cap);
+        if (np == 0) {
+            // no pair: every cell of a regular band is reachable with score 0 and an empty chain (the split-off leading /
+            // trailing deletions of a long contig are such regions, a million diagonals each)
+            if (lane == 0) { a.nmruns[ridx] = 0; a.score[ridx] = 0; }
+            continue;
+        }
         const int32_t *const px = a.px + reg.pair_off, *const py = a.py + reg.pair_off, *const pw = a.pw + reg.pair_off;
 
         // 1. clear

@@ -76,8 +76,11 @@ def test_emulated_kernel_returns_the_checkers_chain(emu, seed):
 
 def test_emulated_kernel_edge_cases(emu):
     # no pairs at all: empty chain, score 0
-    cx, cy, score, env = run_emu(emu, 40, 30, [], [], [])
-    assert len(cx) == 0 and score == 0 and env == 71
+    cx, cy, score, _ = run_emu(emu, 40, 30, [], [], [])
+    assert len(cx) == 0 and score == 0
+    # one pair whose reweighted mass is not positive: unusable, empty chain, and the envelope is the path through it
+    cx, cy, score, env = run_emu(emu, 40, 30, [7], [9], [1000])
+    assert len(cx) == 0 and score == 0 and env < 3 * 71
     # a single pair, pairs in the corners, a one-base read
     cx, cy, score, _ = run_emu(emu, 5, 5, [0, 4], [0, 4], [9000000, 9000000])
     assert list(cx) == [0, 4] and list(cy) == [0, 4]
