@@ -180,6 +180,12 @@ struct Tabs {
     const char *ctab;
 };
 constexpr int TROW = PHMM_TAB_SUM ? 1 : TS;   // doubles per table row
+#ifndef PHMM_TM_T
+#define PHMM_TM_T 0             // 1: the s -> M table transposed, tM[s][pair] (25 doubles per state): a lane's five loads are 8-byte
+#endif                          //    ones whose bank depends on the base pair alone (2 * pair mod 32), instead of 16-byte loads of
+                                //    rows 48 bytes apart that collide whenever two lanes' pairs differ by 8 (bank conflicts are 9 %
+                                //    of the shared-memory wavefronts of k_fb2, profiles/r02p_k_fb2_ncu_metrics.txt)
+constexpr int TMROW = PHMM_TM_T ? 1 : TROW;   // doubles between the entries of two base pairs in the s -> M table
 
 // One column of 5 state values.  GUARD: scalar loads through an in-band test (any buffer, any stride);
 // otherwise unguarded loads (16-byte ones when the columns are padded, CS = 6) from a CS-strided shared-memory column whose out-of-band
@@ -244,10 +250,15 @@ __device__ __forceinline__ GapRow ld_gap(const double *r, const DevModel &) {
     return g;
 }
 __device__ __forceinline__ MatRow ld_mat(const double *r, const DevModel &) {
+#if PHMM_TM_T
+    MatRow m; m.m = r[0]; m.sx = r[25]; m.sy = r[50]; m.lx = r[75]; m.ly = r[100];
+    return m;
+#else
     const double2 a = *reinterpret_cast<const double2 *>(r);
     const double2 b = *reinterpret_cast<const double2 *>(r + 2);
     MatRow m; m.m = a.x; m.sx = a.y; m.sy = b.x; m.lx = b.y; m.ly = r[4];
     return m;
+#endif
 }
 #endif
 
@@ -258,7 +269,7 @@ __device__ __forceinline__ void fwd_cell_r(const Tabs &t, const DevModel &md, in
                                            const ColV &C, double UM, double UsX, double UsY, double UlY, double out[NS]) {
     const char *ctab = t.ctab;
     const GapRow gx = ld_gap<SWITCH, true>(t.tX + cX * TROW, md), gy = ld_gap<SWITCH, false>(t.tY + cY * TROW, md);
-    const MatRow gm = ld_mat(t.tM + (cX * 5 + cY) * TROW, md);
+    const MatRow gm = ld_mat(t.tM + (cX * 5 + cY) * TMROW, md);
     {
         double a = LM + gx.s;
         a = LA_G(a, LsX + gx.ss, ctab);
@@ -294,7 +305,7 @@ __device__ __forceinline__ void bwd_cell_r(const Tabs &t, const DevModel &md, in
                                            double BlY, double out[NS]) {
     const char *ctab = t.ctab;
     const GapRow gx = ld_gap<SWITCH, true>(t.tX + cXn * TROW, md), gy = ld_gap<SWITCH, false>(t.tY + cYn * TROW, md);
-    const MatRow gm = ld_mat(t.tM + (cXn * 5 + cYn) * TROW, md);
+    const MatRow gm = ld_mat(t.tM + (cXn * 5 + cYn) * TMROW, md);
     {
         double a = Bm + gm.m;
         a = LA_M(a, BsY + gy.s, ctab);
@@ -498,7 +509,11 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
 #else
     for (int i = tid; i < 25 * TS; i += NTA) {
         const int r = i / TS, s = i - r * TS;
+#if PHMM_TM_T
+        if (s < NS) stM[s * 25 + r] = a.m.eM[r] + a.m.tr[s * 5 + S_M];
+#else
         stM[i] = s < NS ? a.m.eM[r] + a.m.tr[s * 5 + S_M] : 0.0;
+#endif
     }
     if (tid < 5 * TS) {
         const int c = tid / TS, s = tid - c * TS;
