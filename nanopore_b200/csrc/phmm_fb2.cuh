@@ -46,7 +46,12 @@ constexpr int REC_FAST3 = 4;        //   diagonals d-2, d-1, d (+-1 column) fit 
 constexpr int CS = PHMM_CS;               // doubles per shared-memory column: 5 (five resident regions per SM at 512 columns) or 6 (padded: 16-byte loads)
 constexpr int TS = 6;                     // doubles per row of the (emission + transition) tables: 5 used, 16-byte aligned pairs
 constexpr int TG_S = 0, TG_SS = 1, TG_L = 2, TG_LL = 3, TG_SW = 4;   // slots of a gap row: M->s, s->s, M->l, l->l, other s->s (switch)
-constexpr int FB2_TAB = 16 + 25 * TS + 5 * TS + 5 * TS;   // logAdd coefficients + the three (emission + transition) tables
+#ifndef PHMM_TM_T
+#define PHMM_TM_T 2             // layout of the s -> M table, see tm_index / ld_mat
+#endif
+constexpr int TM_PAIRS = PHMM_TM_T == 2 ? 37 : 25;       // entries per state of the transposed table (2: bank-distinct pair index)
+constexpr int TM_DOUBLES = PHMM_TM_T == 2 ? 5 * TM_PAIRS + 1 : 25 * TS;
+constexpr int FB2_TAB = 16 + TM_DOUBLES + 5 * TS + 5 * TS;   // logAdd coefficients + the three (emission + transition) tables
 
 
 // Timing experiments (scripts/tune.py) switch phases of the kernel off and make its results wrong: they exist only in
@@ -168,6 +173,7 @@ __device__ __forceinline__ double logadd_k(double x, double y) {
 #ifndef PHMM_TAB_SUM
 #define PHMM_TAB_SUM 0          // 1: shared memory holds the emissions only; (emission + transition) is added per cell, the
 #endif                          //    transition coming from the kernel parameters (constant bank operand of the DADD)
+                                // 2: that for the two gap tables only (their chains are off a cell's critical path); s -> M stays a table
 
 // Shared-memory tables of (emission + transition) sums, one padded row of CS doubles per symbol (pair); the
 // scalar definition adds `from + (eP + tP)`, so the parenthesised sum can be taken once per model.
@@ -180,12 +186,21 @@ struct Tabs {
     const char *ctab;
 };
 constexpr int TROW = PHMM_TAB_SUM ? 1 : TS;   // doubles per table row
-#ifndef PHMM_TM_T
-#define PHMM_TM_T 0             // 1: the s -> M table transposed, tM[s][pair] (25 doubles per state): a lane's five loads are 8-byte
-#endif                          //    ones whose bank depends on the base pair alone (2 * pair mod 32), instead of 16-byte loads of
-                                //    rows 48 bytes apart that collide whenever two lanes' pairs differ by 8 (bank conflicts are 9 %
-                                //    of the shared-memory wavefronts of k_fb2, profiles/r02p_k_fb2_ncu_metrics.txt)
-constexpr int TMROW = PHMM_TM_T ? 1 : TROW;   // doubles between the entries of two base pairs in the s -> M table
+// PHMM_TM_T: layout of the s -> M table.  0: one 48-byte row per base pair (cX * 5 + cY), read as 16 + 16 + 8 bytes: lanes whose
+// pairs differ by 8 rows collide (16 common rows, 8 bank groups of a 16-byte load).  1: transposed, tM[s][cX * 5 + cY], five 8-byte
+// loads whose bank is 2 * pair mod 32: pairs 16 apart collide.  2: transposed with the pair index cX * 4 + cY (+ 16 when cY is N),
+// so that the 16 A/C/G/T pairs sit in 16 different bank pairs and only N meets a conflict.  (Bank conflicts were 9 % of the
+// shared-memory wavefronts of k_fb2 with layout 0, profiles/r02p_k_fb2_ncu_metrics.txt.)  Measured, same box, 2368 bench reads
+// (profiles/r02x_tune_table_layout.txt): layout 0 1026.6 ms, 1 1025 ms, 2 1009.4 ms at a launch bound of 6; 999.6 / 990.1 / 965.2 ms
+// at a bound of 5 -- layout 2 with 96 registers is 6.3 % faster than what round 2 shipped before.
+constexpr int TMROW = (PHMM_TM_T || PHMM_TAB_SUM == 1) ? 1 : TS;   // doubles between the entries of two base pairs in the s -> M table
+__device__ __forceinline__ int tm_index(int cX, int cY) {
+#if PHMM_TM_T == 2
+    return cX * 4 + cY + (cY >> 2) * 16;      // 0..15 A/C/G/T pairs, 16..19 (N, y), 20 + 4 x (x, N), 36 (N, N)
+#else
+    return (cX * 5 + cY) * TMROW;
+#endif
+}
 
 // One column of 5 state values.  GUARD: scalar loads through an in-band test (any buffer, any stride);
 // otherwise unguarded loads (16-byte ones when the columns are padded, CS = 6) from a CS-strided shared-memory column whose out-of-band
@@ -233,13 +248,6 @@ __device__ __forceinline__ GapRow ld_gap(const double *r, const DevModel &m) {
     g.sw = SWITCH ? e + m.tr[O * 5 + S] : 0.0;
     return g;
 }
-__device__ __forceinline__ MatRow ld_mat(const double *r, const DevModel &m) {
-    const double e = r[0];
-    MatRow q;
-    q.m = e + m.tr[S_M * 5 + S_M]; q.sx = e + m.tr[S_SX * 5 + S_M]; q.sy = e + m.tr[S_SY * 5 + S_M];
-    q.lx = e + m.tr[S_LX * 5 + S_M]; q.ly = e + m.tr[S_LY * 5 + S_M];
-    return q;
-}
 #else
 // Rows of the (emission + transition) tables, loaded as 16-byte pairs.
 template <bool SWITCH, bool ISX>
@@ -249,9 +257,19 @@ __device__ __forceinline__ GapRow ld_gap(const double *r, const DevModel &) {
     GapRow g; g.s = a.x; g.ss = a.y; g.l = b.x; g.ll = b.y; g.sw = SWITCH ? r[TG_SW] : 0.0;
     return g;
 }
+#endif
+#if PHMM_TAB_SUM == 1
+__device__ __forceinline__ MatRow ld_mat(const double *r, const DevModel &m) {
+    const double e = r[0];
+    MatRow q;
+    q.m = e + m.tr[S_M * 5 + S_M]; q.sx = e + m.tr[S_SX * 5 + S_M]; q.sy = e + m.tr[S_SY * 5 + S_M];
+    q.lx = e + m.tr[S_LX * 5 + S_M]; q.ly = e + m.tr[S_LY * 5 + S_M];
+    return q;
+}
+#else
 __device__ __forceinline__ MatRow ld_mat(const double *r, const DevModel &) {
 #if PHMM_TM_T
-    MatRow m; m.m = r[0]; m.sx = r[25]; m.sy = r[50]; m.lx = r[75]; m.ly = r[100];
+    MatRow m; m.m = r[0]; m.sx = r[TM_PAIRS]; m.sy = r[2 * TM_PAIRS]; m.lx = r[3 * TM_PAIRS]; m.ly = r[4 * TM_PAIRS];
     return m;
 #else
     const double2 a = *reinterpret_cast<const double2 *>(r);
@@ -269,7 +287,7 @@ __device__ __forceinline__ void fwd_cell_r(const Tabs &t, const DevModel &md, in
                                            const ColV &C, double UM, double UsX, double UsY, double UlY, double out[NS]) {
     const char *ctab = t.ctab;
     const GapRow gx = ld_gap<SWITCH, true>(t.tX + cX * TROW, md), gy = ld_gap<SWITCH, false>(t.tY + cY * TROW, md);
-    const MatRow gm = ld_mat(t.tM + (cX * 5 + cY) * TMROW, md);
+    const MatRow gm = ld_mat(t.tM + tm_index(cX, cY), md);
     {
         double a = LM + gx.s;
         a = LA_G(a, LsX + gx.ss, ctab);
@@ -305,7 +323,7 @@ __device__ __forceinline__ void bwd_cell_r(const Tabs &t, const DevModel &md, in
                                            double BlY, double out[NS]) {
     const char *ctab = t.ctab;
     const GapRow gx = ld_gap<SWITCH, true>(t.tX + cXn * TROW, md), gy = ld_gap<SWITCH, false>(t.tY + cYn * TROW, md);
-    const MatRow gm = ld_mat(t.tM + (cXn * 5 + cYn) * TMROW, md);
+    const MatRow gm = ld_mat(t.tM + tm_index(cXn, cYn), md);
     {
         double a = Bm + gm.m;
         a = LA_M(a, BsY + gy.s, ctab);
@@ -438,8 +456,9 @@ __device__ __forceinline__ DiagRec ld_rec(const DiagRec *p) {
 }
 
 #ifndef PHMM_MB4
-#define PHMM_MB4 6              // launch bound of the 4-warp kernel: 80 registers (no spills); shared memory still holds 5 blocks per
-#endif                          // SM at 512 columns -- measured +1.5 % over the 96 registers of a bound of 5 (profiles/r02g_tune_warps.txt)
+#define PHMM_MB4 5              // launch bound of the 4-warp kernel: 96 registers; shared memory holds 5 blocks per SM at 512 columns
+#endif                          // anyway.  A bound of 6 (80 registers) measured +1.5 % in profiles/r02g_tune_warps.txt and -2.6 % after the
+                                // later changes (profiles/r02x_tune_table_layout.txt); with the transposed table 5 wins by 4.4 %
 #ifndef PHMM_NW4
 #define PHMM_NW4 4              // warps of the kernel the planner's "4 warps" class launches (tuning builds: 5, 6)
 #endif
@@ -481,7 +500,7 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
     __shared__ __align__(16) double s_tab[FB2_TAB];
     __shared__ __align__(16) DiagRec s_rec[2 * FB2_RQ];
     double *const sct = s_tab;                                                   // 4 rows x (c3 c2 c1 c0)
-    double *const stM = sct + 16, *const stX = stM + 25 * TS, *const stY = stX + 5 * TS;
+    double *const stM = sct + 16, *const stX = stM + TM_DOUBLES, *const stY = stX + 5 * TS;
     DiagRec *const srec = s_rec;                                                 // [2][FB2_RQ]
     __shared__ int s_region;
     __shared__ int s_npairs;
@@ -503,18 +522,21 @@ __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(con
         sct[8] = -0.004605031767994; sct[9] = 0.063427417320019; sct[10] = 0.695956496475118; sct[11] = 0.514272634594009;
         sct[12] = -0.000458661602210; sct[13] = 0.009695946122598; sct[14] = 0.930734667215156; sct[15] = 0.168037164329057;
     }
-#if PHMM_TAB_SUM
-    for (int i = tid; i < 25; i += NTA) stM[i] = a.m.eM[i];
-    if (tid < 5) { stX[tid] = a.m.eX[tid]; stY[tid] = a.m.eY[tid]; }
+#if PHMM_TAB_SUM == 1
+    for (int i = tid; i < 25; i += NTA) stM[PHMM_TM_T == 2 ? tm_index(i / 5, i % 5) : i] = a.m.eM[i];
 #else
     for (int i = tid; i < 25 * TS; i += NTA) {
         const int r = i / TS, s = i - r * TS;
 #if PHMM_TM_T
-        if (s < NS) stM[s * 25 + r] = a.m.eM[r] + a.m.tr[s * 5 + S_M];
+        if (s < NS) stM[s * TM_PAIRS + (PHMM_TM_T == 2 ? tm_index(r / 5, r % 5) : r)] = a.m.eM[r] + a.m.tr[s * 5 + S_M];
 #else
         stM[i] = s < NS ? a.m.eM[r] + a.m.tr[s * 5 + S_M] : 0.0;
 #endif
     }
+#endif
+#if PHMM_TAB_SUM
+    if (tid < 5) { stX[tid] = a.m.eX[tid]; stY[tid] = a.m.eY[tid]; }
+#else
     if (tid < 5 * TS) {
         const int c = tid / TS, s = tid - c * TS;
         // slots TG_S, TG_SS, TG_L, TG_LL, TG_SW

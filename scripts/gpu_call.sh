@@ -1,11 +1,9 @@
-# one GPU-box call of round 2 (tag r02w): full GPU test suite on the shipped library, decode on the 1 Mb contig shape,
-# k_fb2 timing of the transposed s->M table variants, parity tests on the variant
-T=${TAG:-r02w}
+# final GPU-box call of round 2 (tag r02z): the shipped library (s->M table layout 2, launch bound 5, k_decode_w): tests, smoke, bench,
+# launch list, one full ncu capture of k_fb2
+T=${TAG:-r02z}
 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest_gpu.log
-python scripts/decode_compare.py 300 5000 1000000 100 > gpurun_out/${T}_decode_compare_1mb.json 2> gpurun_out/${T}_decode_compare_1mb.err
-for lib in nanopore_b200/libphmm_sm100.so build/libphmm_tmt.so build/libphmm_tmt5.so nanopore_b200/libphmm_sm100.so build/libphmm_tmt.so; do
-  echo "== $lib" >> gpurun_out/${T}_tune.log
-  TUNE_LIB=$lib REPS=3 python scripts/tune.py 2368 "" >> gpurun_out/${T}_tune.log 2>&1
-done
-PHMM_LIB=$PWD/build/libphmm_tmt.so python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/${T}_pytest_tmt.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest_tmt.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_smoke.log
+python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "rc=$?" >> gpurun_out/${T}_bench.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --reads 2960 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/${T}_b_ncu.log 2>&1
+SHIPPED_LIB=1 ncu --set full --clock-control none --import-source on -k regex:k_fb2 -s 1 -c 1 -o gpurun_out/${T}_prof_fb2 -f python scripts/tune.py 740 "" > gpurun_out/${T}_prof_fb2.log 2>&1
 true
