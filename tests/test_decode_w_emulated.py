@@ -91,3 +91,30 @@ def test_emulated_kernel_edge_cases(emu):
     xs = np.arange(40)
     assert run_emu(emu, 60, 60, xs, 39 - xs, np.full(40, 200000)) is None
     assert run_emu(emu, 400, 400, [0, 399], [399, 0], [5000000, 5000000]) is None
+
+
+def test_emulated_kernel_tie_rules_on_random_bands(emu):
+    """Weights in {0, 1, 2} (gap_gamma 0, so the kernel's reweighting leaves them as they are): equal scores everywhere.
+    The kernel never sees the band -- it must still pick the chain the full sweep picks on a random regular band that
+    holds the pairs (tests/test_decode_skip_theory.py::full_sweep)."""
+    import random
+    from test_decode_narrow_theory import random_case
+    from test_decode_skip_theory import full_sweep
+    rng = random.Random(23)
+    n = 0
+    for trial in range(500):
+        case = random_case(rng)
+        if case is None:
+            continue
+        lx, ly, lo, hi, pairs = case
+        want_score, want_ids = full_sweep(lo, hi, lx, ly, pairs)
+        by_id = {k: c for c, (_, k) in pairs.items()}
+        cells = list(pairs)
+        got = run_emu(emu, lx, ly, [c[0] - 1 for c in cells], [c[1] - 1 for c in cells], [pairs[c][0] for c in cells],
+                      gap_gamma=0.0, seed=trial)
+        assert got is not None
+        cx, cy, score, _ = got
+        assert score == want_score, (lx, ly, pairs)
+        assert [(int(x) + 1, int(y) + 1) for x, y in zip(cx, cy)] == [by_id[k] for k in want_ids], (lx, ly, lo, hi, pairs)
+        n += 1
+    assert n > 200
