@@ -73,6 +73,12 @@ constexpr int TOTAL_EVERY = 10;
 
 #define PHMM_NEG_INF (__longlong_as_double(0xfff0000000000000LL))
 
+// The dynamic shared-memory array of a kernel.  tests/tools/warp_emu/ (the host emulation the CPU tests run kernel
+// sources under) defines it as a pointer to a host buffer before including the kernel headers.
+#ifndef PHMM_DYN_SHARED
+#define PHMM_DYN_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 // ---------------------------------------------------------------------------
 // logAdd: sonLib's piecewise-cubic log(exp(x)+exp(y)), Horner
 // steps fused.  Branch-free; bit-exact with the scalar definition:

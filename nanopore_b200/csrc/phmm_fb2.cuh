@@ -492,7 +492,7 @@ template <int NW, bool SWITCH, bool EXPECT>
 __global__ void __launch_bounds__(NW * 32, fb2_min_blocks(NW, EXPECT)) k_fb2(const __grid_constant__ Fb2Args a) {
     constexpr int NC = NW * 32;            // threads; all compute
     constexpr int NTA = NC;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PHMM_DYN_SHARED(smem_raw);
     const int tid = threadIdx.x;
     const int wcap = a.wcap, cmask = wcap - 1;
     double *const sbuf = reinterpret_cast<double *>(smem_raw);                  // [2][wcap][CS]

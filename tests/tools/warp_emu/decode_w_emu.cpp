@@ -4,66 +4,11 @@
 // returns with the checker's.  Test infrastructure only.
 #include <stdio.h>
 #include <stdlib.h>
-#include <ucontext.h>
 #include <vector>
 
 #include "cuda_runtime.h"
+#include "warp_emu.h"
 #include "../../../nanopore_b200/csrc/phmm_decode_w.cuh"
-
-namespace warp_emu {
-unsigned long long slot[32];
-static ucontext_t main_ctx, ctx[32];
-static int cur = 0, done[32];
-static long arrived[32];
-static unsigned order_seed = 1;
-static const phmm::DecWArgs *g_args;
-
-int lane() { return cur; }
-static void yield() { swapcontext(&ctx[cur], &main_ctx); }
-void barrier() {
-    const long g = ++arrived[cur];
-    for (;;) {
-        bool all = true;
-        for (int l = 0; l < 32; l++) if (!done[l] && arrived[l] < g) { all = false; break; }
-        if (all) return;
-        yield();
-    }
-}
-static void entry() {
-    phmm::k_decode_w(*g_args);
-    done[cur] = 1;
-    yield();
-}
-// runs one warp to completion; the order in which runnable lanes are resumed is shuffled per round (seed != 0) so that
-// a missing synchronisation shows as a wrong result for some seed
-static void run_warp(const phmm::DecWArgs &a, unsigned seed) {
-    g_args = &a;
-    order_seed = seed;
-    std::vector<std::vector<char>> stacks(32, std::vector<char>(1 << 18));
-    for (int l = 0; l < 32; l++) {
-        done[l] = 0; arrived[l] = 0;
-        getcontext(&ctx[l]);
-        ctx[l].uc_stack.ss_sp = stacks[l].data();
-        ctx[l].uc_stack.ss_size = stacks[l].size();
-        ctx[l].uc_link = &main_ctx;
-        makecontext(&ctx[l], entry, 0);
-    }
-    int perm[32];
-    for (int l = 0; l < 32; l++) perm[l] = l;
-    for (;;) {
-        bool any = false;
-        if (seed) for (int l = 31; l > 0; l--) { order_seed = order_seed * 1664525u + 1013904223u; const int j = (order_seed >> 8) % (l + 1); std::swap(perm[l], perm[j]); }
-        for (int q = 0; q < 32; q++) {
-            const int l = perm[q];
-            if (done[l]) continue;
-            any = true;
-            cur = l;
-            swapcontext(&main_ctx, &ctx[l]);
-        }
-        if (!any) break;
-    }
-}
-}  // namespace warp_emu
 
 // One region: pairs (px, py, pw) in region-local sequence coordinates.  Returns the number of match runs written
 // (reverse order) or -1 when the kernel left the region to k_decode; *score receives the chain score.
@@ -91,7 +36,7 @@ extern "C" int emu_decode_w(int lx, int ly, int np, const int32_t *px, const int
     a.bx = bx.data(); a.by = by.data(); a.bwr = bwr.data(); a.pred = pred.data(); a.max_pairs = np;
     a.fb_list = fb_list; a.fb_count = &fb_count;
     a.mrx = mrx; a.mry = mry; a.mrn = mrn; a.nmruns = &nmruns; a.score = score;
-    warp_emu::run_warp(a, seed);
+    warp_emu::run_block(32, seed, [&]() { phmm::k_decode_w(a); });
     if (envelope_cells) {
         long c = 0;
         for (int d = 0; d <= nd; d++) c += bhi[d] - blo[d] + 1;
