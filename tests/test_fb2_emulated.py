@@ -27,6 +27,9 @@ def emu(tmp_path_factory):
     lib.emu_fb2_region.restype = C.c_int
     lib.emu_fb2_region.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_double,
                                    C.c_int, C.c_int, C.c_uint, vp, vp, vp, C.c_int, vp]
+    lib.emu_fb2_region_expect.restype = C.c_int
+    lib.emu_fb2_region_expect.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_uint, vp, vp, vp, vp]
     return lib
 
 
@@ -96,3 +99,53 @@ def test_emulated_fb2_variants(emu, warps, wcap):
     b = synth.make_batch(1, 800, 3000, seed=43)
     check_read(emu, b.ref[b.ref_start[0]:b.ref_end[0]], b.read(0), b.ops(0), band=50, warps=warps, wcap=wcap, seed=3,
                min_diags=150, tb_diags=30)
+
+
+def regions_with_runs(ops, lX, lY, split):
+    """(region row, region-local anchor runs) as plan_read() of phmm_api.cu assigns them."""
+    _, _, runs = anchors_and_runs(ops)
+    j, out = 0, []
+    for row in oracle.regions(ops, lX, lY, TRIM, split):
+        x1, y1, x2, y2 = (int(v) for v in row[:4])
+        mine = []
+        while j < len(runs) and runs[j][0] + runs[j][1] < x2 + y2:
+            mine.append((runs[j][0] - x1, runs[j][1] - y1, runs[j][2]))
+            j += 1
+        out.append((row, mine))
+    return out
+
+
+@pytest.mark.parametrize("warps,band,split", [(4, 10, 300), (2, 10, 300), (4, 50, 3000)])
+def test_emulated_estep_integers_equal_the_checkers(emu, warps, band, split):
+    """k_fb2<.., EXPECT>: the 105 expectations in 2^-32 fixed point and the log-likelihood in 2^-20, summed over the
+    regions of a read the way expectations_reduce() of phmm_api.cu does, against po_expectations_fixed."""
+    b = synth.make_batch(2, 700, 700, seed=51, global_form=False)          # EM inputs are global: window = contig (utils.py:492-496)
+    model = oracle.Model()
+    m60 = np.ascontiguousarray(model.dump(), dtype=np.float64)
+    params = oracle.make_params(expansion=band, split_side=split, min_diags=200, tb_diags=40)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for i in range(b.n):
+        X = np.ascontiguousarray(b.ref[b.ref_start[i]:b.ref_end[i]], dtype=np.uint8)
+        Y = np.ascontiguousarray(b.read(i), dtype=np.uint8)
+        acc = [0] * 106
+        cells = 0
+        for row, mine in regions_with_runs(b.ops(i), len(X), len(Y), split):
+            region = np.array([row[0], row[1], row[2], row[3], row[6], row[7]], dtype=np.int64)
+            r = np.array(mine, dtype=np.int32).reshape(-1, 3)
+            T, E = np.zeros(25, dtype=np.uint64), np.zeros(80, dtype=np.uint64)
+            LL, c = C.c_double(0.0), C.c_int64(0)
+            rc = emu.emu_fb2_region_expect(vp(X), len(X), vp(Y), len(Y), vp(region), len(mine), vp(r), vp(m60), band, 200, 40, warps, 0,
+                                           i + 5, vp(T), vp(E), C.byref(LL), C.byref(c))
+            assert rc >= 0
+            cells += c.value
+            for k in range(25):
+                acc[k] += int(T[k])
+            for k in range(80):
+                acc[25 + k] += int(E[k])
+            acc[105] += int(np.rint(LL.value * 1048576.0))
+        hi, lo, want_cells = oracle.expectations_fixed(model, X, Y, b.ops(i), params)
+        assert cells == want_cells
+        for k in range(106):
+            bits = 32 if k < 105 else 20
+            h = acc[k] >> bits
+            assert (h, acc[k] - (h << bits)) == (int(hi[k]), int(lo[k])), "statistic %d differs" % k

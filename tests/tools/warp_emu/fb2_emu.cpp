@@ -18,10 +18,14 @@ static int pow2_at_least(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 // model60: tr[25], eM[25], eX[5], eY[5] in log space (oracle.Model().dump()).  region: x1, y1, x2, y2, ragged_left,
 // ragged_right in window / read coordinates; runs: n_runs x (x, y, n) region-local anchor runs.  Returns the number of
 // posterior pairs (written to px, py, pw in region-local sequence coordinates, unsorted), -1 if cap is too small.
-template <int NW>
+//
+// EXPECT: the Baum-Welch E-step instead (k_fb2<.., true>): expT[25] / expE[80] receive the region's 2^-32 fixed-point counts,
+// expLL its summed log-likelihood; no pairs.
+template <int NW, bool EXPECT>
 static int run_region(const uint8_t *X, int64_t lX, const uint8_t *Y, int64_t lY, const int64_t *region, int n_runs, const int32_t *runs_xyn,
                       const double *model60, int band, int min_diags, int tb_diags, double threshold, int wcap_opt, unsigned seed,
-                      int32_t *px, int32_t *py, int32_t *pw, int cap, int64_t *cells) {
+                      int32_t *px, int32_t *py, int32_t *pw, int cap, int64_t *cells,
+                      unsigned long long *expT = nullptr, unsigned long long *expE = nullptr, double *expLL = nullptr) {
     constexpr int PAD = 16;
     std::vector<uint8_t> refp(lX + 2 * PAD, 4), readp(lY + 2 * PAD, 4);
     memcpy(refp.data() + PAD, X, lX);
@@ -56,19 +60,22 @@ static int run_region(const uint8_t *X, int64_t lX, const uint8_t *Y, int64_t lY
     warp_emu::run_block(1, 0, [&]() { k_geometry(&reg, runs.data(), 1, dp, &geom, tb_off.data(), tbp.data()); });
     *cells = geom.cells;
     if (nd == 0) return 0;
-    // plan (plan_memory of phmm_api.cu for one region, realignment layout: 1 double per cell, 5 more on total diagonals)
+    // plan (plan_memory of phmm_api.cu for one region; realignment layout: 1 double per cell, 5 more on total diagonals;
+    // E-step layout: 10 doubles per live cell, 11 where a total is evaluated)
     const int bw = geom.max_width, wg = pow2_at_least(bw);
     const int wcap = wcap_opt ? wcap_opt : std::max(64, std::min(512, wg));
-    const int64_t ring_doubles = geom.max_live_doubles + 4 * 11 * (int64_t)bw + 16;
+    const int64_t ring_cells = std::max<int64_t>(2, geom.max_live_cells + geom.max_width + 2);
+    const int64_t live_need = EXPECT ? (ring_cells + 2) * 11 : geom.max_live_doubles;
+    const int64_t ring_doubles = live_need + 4 * 11 * (int64_t)bw + 16;
     const int dcap = std::max(4, geom.max_live_diags + 4) + 4, tcap = dcap / TOTAL_EVERY + 4;
     std::vector<int64_t> rec_off = {0, (int64_t)nd + 1};
     std::vector<DiagRec> recs(nd + 8);
     const int32_t *ntb = &geom.tracebacks;
     warp_emu::run_block(1, 0, [&]() {
-        k_records(&reg, runs.data(), 1, dp, tb_off.data(), tbp.data(), ntb, (int)(sizeof(RegionGeom) / 4), ring_doubles, wcap, 1, 5,
-                  rec_off.data(), recs.data());
+        k_records(&reg, runs.data(), 1, dp, tb_off.data(), tbp.data(), ntb, (int)(sizeof(RegionGeom) / 4), ring_doubles, wcap,
+                  EXPECT ? 10 : 1, EXPECT ? 1 : 5, rec_off.data(), recs.data());
     });
-    const int ccap = 2 * cap + 1024;
+    const int ccap = EXPECT ? 1 : 2 * cap + 1024;
     std::vector<double> ring(ring_doubles + 16), wide((size_t)4 * NS * wg + 16), fsave((size_t)2 * CS * wcap + 16), totals((size_t)tcap + wg + 16);
     std::vector<long long> cand(ccap + 16);
     std::vector<unsigned char> smem((size_t)2 * CS * wcap * 8 + 64);
@@ -84,16 +91,29 @@ static int run_region(const uint8_t *X, int64_t lX, const uint8_t *Y, int64_t lY
     a.wide = wide.data(); a.wg = wg; a.fsave = fsave.data(); a.totals = totals.data(); a.tcap = tcap;
     a.cand = cand.data(); a.ccap = ccap; a.est_eps = 0.02; a.wcap = wcap;
     a.px = px; a.py = py; a.pw = pw; a.npairs = &npairs;
+    a.expT = expT; a.expE = expE; a.expLL = expLL;
     warp_emu::dyn_smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
-    if (sw) warp_emu::run_block(NW * 32, seed, [&]() { k_fb2<NW, true, false>(a); });
-    else warp_emu::run_block(NW * 32, seed, [&]() { k_fb2<NW, false, false>(a); });
+    if (sw) warp_emu::run_block(NW * 32, seed, [&]() { k_fb2<NW, true, EXPECT>(a); });
+    else warp_emu::run_block(NW * 32, seed, [&]() { k_fb2<NW, false, EXPECT>(a); });
     return npairs > cap ? -1 : npairs;
 }
 
 extern "C" int emu_fb2_region(const uint8_t *X, int64_t lX, const uint8_t *Y, int64_t lY, const int64_t *region, int n_runs,
                               const int32_t *runs_xyn, const double *model60, int band, int min_diags, int tb_diags, double threshold,
                               int warps, int wcap, unsigned seed, int32_t *px, int32_t *py, int32_t *pw, int cap, int64_t *cells) {
-    if (warps == 2) return run_region<2>(X, lX, Y, lY, region, n_runs, runs_xyn, model60, band, min_diags, tb_diags, threshold, wcap, seed, px, py, pw, cap, cells);
-    if (warps == 8) return run_region<8>(X, lX, Y, lY, region, n_runs, runs_xyn, model60, band, min_diags, tb_diags, threshold, wcap, seed, px, py, pw, cap, cells);
-    return run_region<4>(X, lX, Y, lY, region, n_runs, runs_xyn, model60, band, min_diags, tb_diags, threshold, wcap, seed, px, py, pw, cap, cells);
+    if (warps == 2) return run_region<2, false>(X, lX, Y, lY, region, n_runs, runs_xyn, model60, band, min_diags, tb_diags, threshold, wcap, seed, px, py, pw, cap, cells);
+    if (warps == 8) return run_region<8, false>(X, lX, Y, lY, region, n_runs, runs_xyn, model60, band, min_diags, tb_diags, threshold, wcap, seed, px, py, pw, cap, cells);
+    return run_region<4, false>(X, lX, Y, lY, region, n_runs, runs_xyn, model60, band, min_diags, tb_diags, threshold, wcap, seed, px, py, pw, cap, cells);
+}
+
+extern "C" int emu_fb2_region_expect(const uint8_t *X, int64_t lX, const uint8_t *Y, int64_t lY, const int64_t *region, int n_runs,
+                                     const int32_t *runs_xyn, const double *model60, int band, int min_diags, int tb_diags, int warps,
+                                     int wcap, unsigned seed, unsigned long long *expT, unsigned long long *expE, double *expLL, int64_t *cells) {
+    int32_t dummy[4];
+    if (nullptr == expT || nullptr == expE || nullptr == expLL) return -2;
+    for (int k = 0; k < 25; k++) expT[k] = 0;
+    for (int k = 0; k < 80; k++) expE[k] = 0;
+    *expLL = 0.0;
+    if (warps == 2) return run_region<2, true>(X, lX, Y, lY, region, n_runs, runs_xyn, model60, band, min_diags, tb_diags, 0.01, wcap, seed, dummy, dummy, dummy, 1, cells, expT, expE, expLL);
+    return run_region<4, true>(X, lX, Y, lY, region, n_runs, runs_xyn, model60, band, min_diags, tb_diags, 0.01, wcap, seed, dummy, dummy, dummy, 1, cells, expT, expE, expLL);
 }
