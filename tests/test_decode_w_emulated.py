@@ -118,3 +118,111 @@ def test_emulated_kernel_tie_rules_on_random_bands(emu):
         assert [(int(x) + 1, int(y) + 1) for x, y in zip(cx, cy)] == [by_id[k] for k in want_ids], (lx, ly, lo, hi, pairs)
         n += 1
     assert n > 200
+
+
+# ---- the block-per-region kernel k_decode<2> (takes the regions k_decode_w leaves) under the same emulation ----
+@pytest.fixture(scope="module")
+def emu_block(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("warp_emu") / "libdecode_emu.so")
+    subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-I", EMU_DIR, "-o", out,
+                           os.path.join(EMU_DIR, "decode_emu.cpp")])
+    lib = C.CDLL(out)
+    vp = C.c_void_p
+    lib.emu_decode_block.restype = C.c_int
+    lib.emu_decode_block.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, C.c_double, C.c_double, C.c_int,
+                                     C.c_uint, vp, vp, vp, C.c_int, vp, vp]
+    return lib
+
+
+def run_block_emu(lib, lx, ly, runs, band, px, py, pw, gap_gamma=0.5, full_sweep=0, seed=0):
+    px, py, pw = (np.ascontiguousarray(v, dtype=np.int32) for v in (px, py, pw))
+    r = np.ascontiguousarray(np.array(runs, dtype=np.int32).reshape(-1, 3))
+    cap = min(lx, ly) + 1
+    mrx, mry, mrn = (np.zeros(cap, dtype=np.int32) for _ in range(3))
+    score, regular = C.c_int64(0), C.c_int32(-1)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = lib.emu_decode_block(lx, ly, len(r), vp(r), band, len(px), vp(px), vp(py), vp(pw), gap_gamma, 0.0, full_sweep, seed,
+                             vp(mrx), vp(mry), vp(mrn), cap, C.byref(score), C.byref(regular))
+    cx, cy = [], []
+    for k in range(n - 1, -1, -1):
+        cx.extend(range(mrx[k], mrx[k] + mrn[k]))
+        cy.extend(range(mry[k], mry[k] + mrn[k]))
+    return np.array(cx, dtype=np.int64), np.array(cy, dtype=np.int64), score.value, regular.value
+
+
+def anchor_runs(ops, trim=14):
+    runs, x, y = [], 0, 0
+    for o in ops:
+        ln, code = int(o) >> 2, int(o) & 3
+        if code == 0:
+            if ln > 2 * trim:
+                runs.append((x + trim, y + trim, ln - 2 * trim))
+            x += ln; y += ln
+        elif code == 1:
+            y += ln
+        else:
+            x += ln
+    return runs
+
+
+@pytest.mark.parametrize("full_sweep", [0, 1])
+def test_emulated_block_kernel_returns_the_checkers_chain(emu_block, full_sweep):
+    b = synth.make_batch(3, 1200, 5000, seed=31)
+    model, params = oracle.Model(), oracle.make_params(expansion=50)
+    n = 0
+    for i in range(b.n):
+        X = b.ref[b.ref_start[i]:b.ref_end[i]]
+        if len(oracle.regions(b.ops(i), len(X), len(b.read(i)), 14, 3000)) != 1:
+            continue
+        want = oracle.realign(model, X, b.read(i), b.ops(i), params)
+        cx, cy, score, regular = run_block_emu(emu_block, len(X), len(b.read(i)), anchor_runs(b.ops(i)), 50, want["px"], want["py"],
+                                               want["pw"], full_sweep=full_sweep, seed=i + 1)
+        assert regular == 1
+        assert score == want["mea_score"] and np.array_equal(cx, want["cx"]) and np.array_equal(cy, want["cy"])
+        n += 1
+    assert n >= 2
+
+
+def test_both_emulated_kernels_agree_under_ties(emu, emu_block):
+    """Random pairs with weights in {0, 1, 2} inside the band of a few anchor runs: k_decode<2> with and without its
+    skipping, k_decode_w (which never sees the band) and the plain-Python full sweep pick the same chain."""
+    import random
+    from test_decode_skip_theory import full_sweep
+    rng = random.Random(29)
+    n = 0
+    for trial in range(120):
+        lx, ly = rng.randint(20, 90), rng.randint(20, 90)
+        # two or three anchor runs along a staircase, band 4..10
+        runs, x, y = [], rng.randint(0, 5), rng.randint(0, 5)
+        for _ in range(rng.randint(1, 3)):
+            ln = rng.randint(2, 8)
+            if x + ln >= lx or y + ln >= ly:
+                break
+            runs.append((x, y, ln))
+            x += ln + rng.randint(1, 25); y += ln + rng.randint(1, 25)
+        band = 2 * rng.randint(2, 5)
+        ax = np.array([r[0] + k for r in runs for k in range(r[2])], dtype=np.int64)
+        ay = np.array([r[1] + k for r in runs for k in range(r[2])], dtype=np.int64)
+        L, R = oracle.band(ax, ay, lx, ly, band)
+        d = np.arange(lx + ly + 1)
+        lo, hi = ((d + L) // 2).tolist(), ((d + R) // 2).tolist()
+        cells = [(xx, dd - xx) for dd in range(2, lx + ly + 1) for xx in range(lo[dd], hi[dd] + 1)
+                 if xx >= 1 and dd - xx >= 1 and lo[dd - 2] <= xx - 1 <= hi[dd - 2]]
+        if len(cells) < 4:
+            continue
+        centre = rng.choice(cells)
+        near = [c for c in cells if abs(c[0] + c[1] - centre[0] - centre[1]) <= rng.randint(1, 10)] + rng.sample(cells, 2)
+        chosen = list(dict.fromkeys(rng.sample(near, min(len(near), rng.randint(1, 14)))))
+        pairs = {c: (rng.choice([0, 1, 1, 2]), k) for k, c in enumerate(chosen)}
+        want_score, want_ids = full_sweep(lo, hi, lx, ly, pairs)
+        by_id = {k: c for c, (_, k) in pairs.items()}
+        want_chain = [by_id[k] for k in want_ids]
+        args = ([c[0] - 1 for c in chosen], [c[1] - 1 for c in chosen], [pairs[c][0] for c in chosen])
+        for fs in (0, 1):
+            cx, cy, score, regular = run_block_emu(emu_block, lx, ly, runs, band, *args, gap_gamma=0.0, full_sweep=fs, seed=trial + 1)
+            assert regular == 1
+            assert score == want_score and [(int(a) + 1, int(b_) + 1) for a, b_ in zip(cx, cy)] == want_chain, (lx, ly, runs, band, pairs, fs)
+        cx, cy, score, _ = run_emu(emu, lx, ly, *args, gap_gamma=0.0, seed=trial + 1)
+        assert score == want_score and [(int(a) + 1, int(b_) + 1) for a, b_ in zip(cx, cy)] == want_chain
+        n += 1
+    assert n > 60
