@@ -27,6 +27,8 @@ def emu(tmp_path_factory):
     lib.emu_fb2_region.restype = C.c_int
     lib.emu_fb2_region.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_double,
                                    C.c_int, C.c_int, C.c_uint, vp, vp, vp, C.c_int, vp]
+    lib.emu_fwdbwd_region.restype = C.c_int
+    lib.emu_fwdbwd_region.argtypes = lib.emu_fb2_region.argtypes
     lib.emu_fb2_region_expect.restype = C.c_int
     lib.emu_fb2_region_expect.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_uint, vp, vp, vp, vp]
@@ -51,7 +53,7 @@ def anchors_and_runs(ops):
     return np.array(ax, dtype=np.int64), np.array(ay, dtype=np.int64), runs
 
 
-def check_read(lib, X, Y, ops, band, warps=4, wcap=0, seed=0, min_diags=1000, tb_diags=40, threshold=0.01):
+def check_read(lib, X, Y, ops, band, warps=4, wcap=0, seed=0, min_diags=1000, tb_diags=40, threshold=0.01, kernel="emu_fb2_region"):
     model = oracle.Model()
     params = oracle.make_params(expansion=band, min_diags=min_diags, tb_diags=tb_diags, threshold=threshold)
     m60 = np.ascontiguousarray(model.dump(), dtype=np.float64)
@@ -70,7 +72,7 @@ def check_read(lib, X, Y, ops, band, warps=4, wcap=0, seed=0, min_diags=1000, tb
         r = np.array(mine, dtype=np.int32).reshape(-1, 3)
         cells = C.c_int64(0)
         vp = lambda a: a.ctypes.data_as(C.c_void_p)
-        n = lib.emu_fb2_region(vp(X), len(X), vp(Y), len(Y), vp(region), len(mine), vp(r), vp(m60), band, min_diags, tb_diags,
+        n = getattr(lib, kernel)(vp(X), len(X), vp(Y), len(Y), vp(region), len(mine), vp(r), vp(m60), band, min_diags, tb_diags,
                                threshold, warps, wcap, seed, vp(px), vp(py), vp(pw), cap, C.byref(cells))
         assert n >= 0
         assert cells.value == want["cells"]
@@ -99,6 +101,14 @@ def test_emulated_fb2_variants(emu, warps, wcap):
     b = synth.make_batch(1, 800, 3000, seed=43)
     check_read(emu, b.ref[b.ref_start[0]:b.ref_end[0]], b.read(0), b.ops(0), band=50, warps=warps, wcap=wcap, seed=3,
                min_diags=150, tb_diags=30)
+
+
+@pytest.mark.parametrize("warps", [1, 2, 4])
+def test_emulated_first_generation_kernel(emu, warps):
+    """k_fwdbwd (option legacy_kernel; the fall-back for E-step windows too long for the windowed kernel's ring)."""
+    b = synth.make_batch(1, 700, 2500, seed=44)
+    check_read(emu, b.ref[b.ref_start[0]:b.ref_end[0]], b.read(0), b.ops(0), band=20, warps=warps, seed=warps, min_diags=200,
+               tb_diags=40, kernel="emu_fwdbwd_region")
 
 
 def regions_with_runs(ops, lX, lY, split):

@@ -117,3 +117,69 @@ extern "C" int emu_fb2_region_expect(const uint8_t *X, int64_t lX, const uint8_t
     if (warps == 2) return run_region<2, true>(X, lX, Y, lY, region, n_runs, runs_xyn, model60, band, min_diags, tb_diags, 0.01, wcap, seed, dummy, dummy, dummy, 1, cells, expT, expE, expLL);
     return run_region<4, true>(X, lX, Y, lY, region, n_runs, runs_xyn, model60, band, min_diags, tb_diags, 0.01, wcap, seed, dummy, dummy, dummy, 1, cells, expT, expE, expLL);
 }
+
+// The first-generation kernel k_fwdbwd<NW> (whole forward window in HBM; option legacy_kernel and the fall-back for very
+// long E-step windows): one region, planning as plan_memory() does for it.
+template <int NW>
+static int run_region_legacy(const uint8_t *X, int64_t lX, const uint8_t *Y, int64_t lY, const int64_t *region, int n_runs, const int32_t *runs_xyn,
+                             const double *model60, int band, int min_diags, int tb_diags, double threshold, unsigned seed,
+                             int32_t *px, int32_t *py, int32_t *pw, int cap, int64_t *cells) {
+    constexpr int PAD = 16;
+    std::vector<uint8_t> refp(lX + 2 * PAD, 4), readp(lY + 2 * PAD, 4);
+    memcpy(refp.data() + PAD, X, lX);
+    memcpy(readp.data() + PAD, Y, lY);
+    Region reg;
+    memset(&reg, 0, sizeof(reg));
+    reg.xoff = region[0]; reg.yoff = region[1];
+    reg.lx = (int32_t)(region[2] - region[0]); reg.ly = (int32_t)(region[3] - region[1]);
+    reg.ragged_left = (int32_t)region[4]; reg.ragged_right = (int32_t)region[5];
+    reg.nrun = n_runs; reg.pair_cap = cap;
+    std::vector<Run> runs(n_runs + 1);
+    for (int i = 0; i < n_runs; i++) runs[i] = Run{runs_xyn[3 * i], runs_xyn[3 * i + 1], runs_xyn[3 * i + 2]};
+    DevParams dp;
+    memset(&dp, 0, sizeof(dp));
+    dp.expansion = band; dp.min_diags = min_diags; dp.tb_diags = tb_diags;
+    dp.threshold = threshold; dp.lp_skip = threshold > 0.0 ? log(threshold) - 1e-3 : -INFINITY;
+    DevModel m;
+    memset(&m, 0, sizeof(m));
+    memcpy(m.tr, model60, 25 * 8); memcpy(m.eM, model60 + 25, 25 * 8); memcpy(m.eX, model60 + 50, 5 * 8); memcpy(m.eY, model60 + 55, 5 * 8);
+    for (int s = 0; s < 5; s++) m.endp[s] = m.tr[s * 5 + S_M];
+    m.rendp[S_M] = m.tr[S_M * 5 + S_LX]; m.rendp[S_SX] = m.tr[S_M * 5 + S_LX]; m.rendp[S_SY] = m.tr[S_M * 5 + S_LY];
+    m.rendp[S_LX] = m.tr[S_LX * 5 + S_LX]; m.rendp[S_LY] = m.tr[S_LY * 5 + S_LY];
+    const bool sw = m.tr[S_SX * 5 + S_SY] != -INFINITY || m.tr[S_SY * 5 + S_SX] != -INFINITY;
+    m.has_switch = sw;
+    const int nd = reg.lx + reg.ly;
+    const int64_t gap = std::max<int64_t>(1, (int64_t)min_diags - tb_diags - 1);
+    std::vector<int64_t> tb_off = {0, nd / gap + 2};
+    std::vector<int32_t> tbp(tb_off[1] + 4, 0);
+    RegionGeom geom;
+    memset(&geom, 0, sizeof(geom));
+    warp_emu::run_block(1, 0, [&]() { k_geometry(&reg, runs.data(), 1, dp, &geom, tb_off.data(), tbp.data()); });
+    *cells = geom.cells;
+    if (nd == 0) return 0;
+    const int64_t ring_cells = std::max<int64_t>(2, geom.max_live_cells + geom.max_width + 2);
+    const int dcap = std::max(4, geom.max_live_diags + 4), bw = std::max(1, geom.max_width);
+    std::vector<double> fring((size_t)ring_cells * NS + 16), bring((size_t)3 * bw * NS + 16), dots((size_t)2 * bw + 16);
+    std::vector<DiagRec> dtab(dcap + 4);
+    int32_t order = 0, counter = 0, npairs = 0;
+    FbArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ref = refp.data() + PAD; a.reads = readp.data() + PAD;
+    a.regions = &reg; a.runs = runs.data(); a.order = &order; a.n_regions = 1; a.counter = &counter;
+    a.m = m; a.p = dp;
+    a.fring = fring.data(); a.ring_cells = ring_cells; a.dtab = dtab.data(); a.dcap = dcap;
+    a.bring = bring.data(); a.bw = bw; a.dots = dots.data();
+    a.px = px; a.py = py; a.pw = pw; a.npairs = &npairs;
+    if (sw) warp_emu::run_block(NW * 32, seed, [&]() { k_fwdbwd<NW, true, false>(a); });
+    else warp_emu::run_block(NW * 32, seed, [&]() { k_fwdbwd<NW, false, false>(a); });
+    return npairs > cap ? -1 : npairs;
+}
+
+extern "C" int emu_fwdbwd_region(const uint8_t *X, int64_t lX, const uint8_t *Y, int64_t lY, const int64_t *region, int n_runs,
+                                 const int32_t *runs_xyn, const double *model60, int band, int min_diags, int tb_diags, double threshold,
+                                 int warps, int wcap_unused, unsigned seed, int32_t *px, int32_t *py, int32_t *pw, int cap, int64_t *cells) {
+    (void)wcap_unused;
+    if (warps == 1) return run_region_legacy<1>(X, lX, Y, lY, region, n_runs, runs_xyn, model60, band, min_diags, tb_diags, threshold, seed, px, py, pw, cap, cells);
+    if (warps == 2) return run_region_legacy<2>(X, lX, Y, lY, region, n_runs, runs_xyn, model60, band, min_diags, tb_diags, threshold, seed, px, py, pw, cap, cells);
+    return run_region_legacy<4>(X, lX, Y, lY, region, n_runs, runs_xyn, model60, band, min_diags, tb_diags, threshold, seed, px, py, pw, cap, cells);
+}
